@@ -1,0 +1,116 @@
+/* include/msckf_b200.h -- C-ABI of the B200 MSCKF measurement-update engine (libmsckf_b200.so).
+ *
+ * The reference (daniilidis-group/msckf_mono) has no plugin / FFI boundary: its filter is the header-only
+ * C++ class template msckf_mono::MSCKF<_S> (include/msckf_mono/msckf.h:31-1512).  This C-ABI is what the
+ * replacement class of the same name (include/msckf_mono/msckf.h in THIS repo) binds: each entry point below
+ * names the reference member function(s) whose numerics it replaces.  All integer bookkeeping (track lists,
+ * clone ids, pruning decisions) stays on the host in the class shim, exactly as in the reference.
+ *
+ * Conventions: plain pointers and sizes only.  `dtype` selects the scalar type of every `void*` array
+ * (MSCKF_B200_F32: float, MSCKF_B200_F64: double) -- the reference's template parameter _S.  Quaternions are
+ * (x,y,z,w) (Eigen coeffs() order).  Error-state order: IMU [dtheta, db_g, dv, db_a, dp] then per clone
+ * [dtheta_C, dp_C] (msckf.h:885-889, :1376-1390).  Every function returns 0 on success, a negative
+ * msckf_b200_status otherwise; there is NO CPU fallback -- a failed device call is a hard error.
+ * A handle owns its device buffers and one CUDA stream; calls on one handle must be serialised by the
+ * caller (like the reference class), different handles are independent.
+ */
+#ifndef MSCKF_B200_H_
+#define MSCKF_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum msckf_b200_dtype { MSCKF_B200_F32 = 0, MSCKF_B200_F64 = 1 };
+enum msckf_b200_status {
+  MSCKF_B200_OK = 0,
+  MSCKF_B200_ERR_CUDA = -1,      /* a CUDA runtime call or kernel failed */
+  MSCKF_B200_ERR_CAPACITY = -2,  /* more clones / tracks / observations than msckf_b200_create reserved */
+  MSCKF_B200_ERR_ARG = -3,       /* invalid argument (e.g. track longer than 98 observations, msckf.h:91) */
+  MSCKF_B200_ERR_NO_DEVICE = -4, /* no CUDA device: the engine never computes on the CPU */
+  MSCKF_B200_ERR_STATE = -5      /* call order violated */
+};
+enum msckf_b200_mode {
+  MSCKF_B200_MARGINALIZE = 0, /* MSCKF::marginalize() msckf.h:336-449: loop A + loop B + measurementUpdate */
+  MSCKF_B200_TRIANGULATE = 1, /* checkMotion :980-1025 + initializePosition :1147-1285 only (pruneRedundantStates :488-531) */
+  MSCKF_B200_RESIDUALIZE = 2  /* loop B + measurementUpdate at caller-given p_f_G (pruneRedundantStates :545-614) */
+};
+
+typedef struct msckf_b200_engine msckf_b200_engine;
+
+typedef struct {
+  int dtype;       /* msckf_b200_dtype */
+  int device;      /* CUDA device ordinal */
+  int max_clones;  /* capacity M_max (covariance is (15+6*M_max)^2) */
+  int max_tracks;  /* capacity of one track batch */
+  int max_obs;     /* capacity of one batch's total observation count */
+} msckf_b200_config;
+
+/* One batch of feature tracks, flat SoA (types.h:102-113 featureTrackToResidualize without the clone copies:
+ * the clone poses are device resident and addressed by POSITION in the sliding window, msckf.h:1481). */
+typedef struct {
+  int n_tracks;
+  const int* obs_offset;  /* [n_tracks+1] prefix offsets into obs / clone_index */
+  const void* obs;        /* [2*obs_offset[n_tracks]] normalised image coordinates (u,v), dtype scalars */
+  const int* clone_index; /* [obs_offset[n_tracks]] positional index of the observing clone */
+  const void* p_f_G;      /* MSCKF_B200_RESIDUALIZE only: [3*n_tracks] feature positions; else NULL */
+} msckf_b200_tracks;
+
+/* Per-track results; every pointer may be NULL (not wanted).  Caller-owned host buffers of n_tracks entries. */
+typedef struct {
+  int* cm_ok;    /* checkMotion result */
+  int* tri_ok;   /* initializePosition validity */
+  int* valid;    /* valid_tracks[] of msckf.h:348 */
+  int* accepted; /* passed gatingTest */
+  void* gamma;   /* Mahalanobis distance, dtype scalars */
+  void* p_f_G;   /* [3*n_tracks] triangulated position, dtype scalars */
+  int m;         /* out: stacked rows of accepted tracks (stack_counter, msckf.h:443) */
+  int rank;      /* out: independent rows kept by the compression */
+} msckf_b200_report;
+
+int msckf_b200_create(const msckf_b200_config* cfg, msckf_b200_engine** out);
+int msckf_b200_destroy(msckf_b200_engine* e);
+
+/* MSCKF::initialize msckf.h:72-97.
+ * camera: q_CI[4], p_C_I[3]; noise: u_var_prime, v_var_prime, Q_imu[144], initial_imu_covar[225] (row-major);
+ * params: max_gn_cost_norm, translation_threshold; imu_state: p_I_G[3], v_I_G[3], b_g[3], b_a[3], g[3], q_IG[4]. */
+int msckf_b200_initialize(msckf_b200_engine* e, const void* camera, const void* noise, const void* params, const void* imu_state);
+/* MSCKF::propagate msckf.h:101-145.  reading: omega[3], a[3], dT */
+int msckf_b200_propagate(msckf_b200_engine* e, const void* reading);
+/* MSCKF::augmentState msckf.h:148-212 (numeric part: clone pose + covariance augmentation) */
+int msckf_b200_augment(msckf_b200_engine* e);
+/* marginalize / pruneRedundantStates numerics, asynchronous on the handle's stream.  The input arrays are
+ * copied to pinned staging before return; results are fetched (and the stream synchronised) by _fetch. */
+int msckf_b200_update_async(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks);
+int msckf_b200_fetch(msckf_b200_engine* e, msckf_b200_report* report);
+/* update_async + fetch */
+int msckf_b200_update(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks, msckf_b200_report* report);
+/* covariance / pose gather of pruneEmptyStates msckf.h:685-761 and pruneRedundantStates :616-681:
+ * keep[] = ascending positional indices of the clones that survive */
+int msckf_b200_prune(msckf_b200_engine* e, const int* keep, int n_keep);
+
+int msckf_b200_num_clones(msckf_b200_engine* e);
+/* imu: p,v,b_g,b_a,g,q_IG, p_null,v_null,q_null (29 scalars); clone_poses: [M*7] p(3) q(4).  Either may be NULL. */
+int msckf_b200_get_state(msckf_b200_engine* e, void* imu, void* clone_poses);
+/* full (15+6M)^2 covariance, row-major, dtype scalars */
+int msckf_b200_get_covariance(msckf_b200_engine* e, void* out);
+/* counters[0..7]: num_feature_tracks_residualized_, pfg_shifted, pfg_oob, n_updates, last m, last rank, 0, 0 */
+int msckf_b200_get_counters(msckf_b200_engine* e, long long* counters);
+/* last delta-x (fp64), returns its length */
+int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap);
+/* option keys: 0 = rank threshold of the compression (relative pivot, default 1e-10) */
+int msckf_b200_set_option(msckf_b200_engine* e, int key, double value);
+/* checkpoint / resume: copy the complete filter state of src into dst (same dtype and capacities) */
+int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src);
+/* number of kernels launched by this handle so far (bench.py's gpu_launches) */
+long long msckf_b200_launch_count(const msckf_b200_engine* e);
+/* the handle's cudaStream_t (for event timing on the launching stream) */
+void* msckf_b200_stream(msckf_b200_engine* e);
+int msckf_b200_synchronize(msckf_b200_engine* e);
+const char* msckf_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSCKF_B200_H_ */

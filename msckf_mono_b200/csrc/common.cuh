@@ -1,0 +1,142 @@
+// msckf_mono_b200/csrc/common.cuh -- device helpers shared by all kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cmath>
+
+namespace mb {
+
+constexpr int kImuDim = 15;
+constexpr int kPoseStride = 8;  // q(x,y,z,w), p(x,y,z), pad  -> 32 B (fp32) / 64 B (fp64): TMA friendly
+
+// Device-resident filter state that is not a matrix (mirrors types.h:70-77 imuState + camera/noise/params).
+template <class S>
+struct DevState {
+  S q_IG[4], b_g[3], v_I_G[3], b_a[3], p_I_G[3], g[3];
+  S q_IG_null[4], v_I_G_null[3], p_I_G_null[3];
+  S q_CI[4], p_C_I[3];
+  S u_var, v_var;
+  S max_gn_cost_norm, translation_threshold;
+  S Q_imu[144];
+  S chi2[99];
+  unsigned long long num_residualized;  // msckf.h:42 num_feature_tracks_residualized_
+  unsigned long long pfg_shifted, pfg_oob, n_updates;
+  int last_m, last_rank, last_status, pad_;
+  double last_dx_norm;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <class S> __device__ __forceinline__ S tsqrt(S x);
+template <> __device__ __forceinline__ float tsqrt<float>(float x) { return sqrtf(x); }
+template <> __device__ __forceinline__ double tsqrt<double>(double x) { return sqrt(x); }
+template <class S> __device__ __forceinline__ S tabs(S x) { return x < S(0) ? -x : x; }
+
+// Eigen QuaternionBase::toRotationMatrix restated; q = (x,y,z,w); R row-major 3x3.
+template <class S>
+__device__ __forceinline__ void quat_to_rot(const S* q, S* R) {
+  const S x = q[0], y = q[1], z = q[2], w = q[3];
+  const S tx = S(2) * x, ty = S(2) * y, tz = S(2) * z;
+  const S twx = tx * w, twy = ty * w, twz = tz * w;
+  const S txx = tx * x, txy = ty * x, txz = tz * x;
+  const S tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = S(1) - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = S(1) - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = S(1) - (txx + tyy);
+}
+template <class S>
+__device__ __forceinline__ void quat_mul(const S* a, const S* b, S* r) {  // Hamilton a*b, (x,y,z,w)
+  const S ax = a[0], ay = a[1], az = a[2], aw = a[3], bx = b[0], by = b[1], bz = b[2], bw = b[3];
+  r[0] = aw * bx + ax * bw + ay * bz - az * by;
+  r[1] = aw * by + ay * bw + az * bx - ax * bz;
+  r[2] = aw * bz + az * bw + ax * by - ay * bx;
+  r[3] = aw * bw - ax * bx - ay * by - az * bz;
+}
+template <class S>
+__device__ __forceinline__ void quat_normalize(S* q) {
+  const S n = tsqrt<S>(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+// Eigen _transformVector with the inverse quaternion q^-1 = conj(q)/|q|^2
+template <class S>
+__device__ __forceinline__ void quat_inv_rotate(const S* q, const S* v, S* out) {
+  const S n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  const S qi[4] = {-q[0] / n2, -q[1] / n2, -q[2] / n2, q[3] / n2};
+  S uv[3] = {qi[1] * v[2] - qi[2] * v[1], qi[2] * v[0] - qi[0] * v[2], qi[0] * v[1] - qi[1] * v[0]};
+  uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+  out[0] = v[0] + qi[3] * uv[0] + (qi[1] * uv[2] - qi[2] * uv[1]);
+  out[1] = v[1] + qi[3] * uv[1] + (qi[2] * uv[0] - qi[0] * uv[2]);
+  out[2] = v[2] + qi[3] * uv[2] + (qi[0] * uv[1] - qi[1] * uv[0]);
+}
+// msckf.h:851-872 buildUpdateQuat
+template <class S>
+__device__ __forceinline__ void build_update_quat(const S* dth, S* u) {
+  const S d0 = S(0.5) * dth[0], d1 = S(0.5) * dth[1], d2 = S(0.5) * dth[2];
+  const S cs = d0 * d0 + d1 * d1 + d2 * d2;
+  u[3] = (cs > S(1)) ? S(1) : tsqrt<S>(S(1) - cs);
+  u[0] = -d0; u[1] = -d1; u[2] = -d2;
+  quat_normalize(u);
+}
+
+// ---- TMA (bulk async copy) staging of a small contiguous table into shared memory -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned phase) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
+  while (!mbar_try_wait(bar, phase)) {
+  }
+}
+// bytes must be a multiple of 16, both addresses 16-byte aligned.  SASS: UBLKCP.
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// Called by all threads of the CTA: thread 0 issues the bulk copy, everybody waits for completion.
+__device__ __forceinline__ void stage_table_tma(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, bytes);
+    tma_bulk_g2s(smem_dst, gmem_src, bytes, bar);
+  }
+  mbar_wait(bar, 0);
+}
+
+}  // namespace mb

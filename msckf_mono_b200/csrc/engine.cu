@@ -1,0 +1,504 @@
+// msckf_mono_b200/csrc/engine.cu -- host side of the B200 engine and the C-ABI of include/msckf_b200.h.
+// One handle = one filter: device-resident covariance / clone poses / IMU state, one CUDA stream,
+// pinned staging for the per-call track batch and report.  No CPU fallback anywhere.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/msckf_b200.h"
+#include "common.cuh"
+#include "feature_kernels.cuh"
+#include "gram_kernels.cuh"
+#include "state_kernels.cuh"
+#include "tail_kernels.cuh"
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(MSCKF_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+constexpr int kMaxSplit = 16;
+constexpr size_t kSmemBudget = 220 * 1024;
+
+static const double kChi2_005[99] = {
+#include "chi2_table.inc"
+};
+
+struct EngineBase {
+  virtual ~EngineBase() {}
+  virtual int initialize(const void*, const void*, const void*, const void*) = 0;
+  virtual int propagate(const void*) = 0;
+  virtual int augment() = 0;
+  virtual int update_async(int mode, const msckf_b200_tracks*) = 0;
+  virtual int fetch(msckf_b200_report*) = 0;
+  virtual int prune(const int*, int) = 0;
+  virtual int get_state(void*, void*) = 0;
+  virtual int get_covariance(void*) = 0;
+  virtual int get_counters(long long*) = 0;
+  virtual int last_dx(double*, int) = 0;
+  virtual int copy_from(const EngineBase*) = 0;
+  virtual int sync() = 0;
+  int dtype = 0, device = 0, Mmax = 0, Tmax = 0, Omax = 0;
+  int M = 0;
+  double rank_thr = 1e-10;
+  long long launches = 0;
+  cudaStream_t stream = nullptr;
+};
+
+template <class S>
+struct Engine : EngineBase {
+  // device
+  mb::DevState<S>* d_st = nullptr;
+  S *d_P = nullptr, *d_P2 = nullptr, *d_poses = nullptr, *d_poses2 = nullptr;
+  int *d_off = nullptr, *d_idx = nullptr, *d_cm = nullptr, *d_tri = nullptr, *d_valid = nullptr, *d_src = nullptr,
+      *d_accept = nullptr, *d_rows = nullptr, *d_rowoff = nullptr, *d_scratch = nullptr, *d_keep = nullptr, *d_m = nullptr,
+      *d_rank = nullptr, *d_keepclones = nullptr;
+  S *d_obs = nullptr, *d_pfg = nullptr, *d_pfg_given = nullptr, *d_gamma = nullptr, *d_Xg = nullptr, *d_rg = nullptr,
+    *d_Vg = nullptr, *d_taug = nullptr;
+  double *d_Z = nullptr, *d_Yq = nullptr, *d_ur = nullptr, *d_G1p = nullptr, *d_G2p = nullptr, *d_D1 = nullptr, *d_D2 = nullptr,
+         *d_bb = nullptr, *d_T2 = nullptr, *d_R2 = nullptr, *d_r2 = nullptr, *d_TP = nullptr, *d_S2 = nullptr, *d_W = nullptr,
+         *d_y = nullptr, *d_dx = nullptr;
+  // pinned host
+  int *h_off = nullptr, *h_idx = nullptr, *h_flags = nullptr /*cm,tri,valid,accept: 4*Tmax*/, *h_mr = nullptr /*m, rank*/;
+  S *h_obs = nullptr, *h_pfg_in = nullptr, *h_pfg = nullptr, *h_gamma = nullptr;
+  mb::DevState<S>* h_st = nullptr;
+  int nmax = 0, ldp = 0, ld = 0;
+  int pending_n = 0, pending_mode = -1;
+  bool initialized = false;
+
+  int alloc() {
+    nmax = 15 + 6 * Mmax;
+    ldp = (nmax + 3) & ~3;
+    ld = (nmax + 1) & ~1;
+    const int cmax = 6 * Mmax;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&d_st, sizeof(mb::DevState<S>)));
+    CK(cudaMalloc(&d_P, sizeof(S) * (size_t)ldp * nmax));
+    CK(cudaMalloc(&d_P2, sizeof(S) * (size_t)ldp * nmax));
+    CK(cudaMalloc(&d_poses, sizeof(S) * mb::kPoseStride * (size_t)(Mmax + 1)));
+    CK(cudaMalloc(&d_poses2, sizeof(S) * mb::kPoseStride * (size_t)(Mmax + 1)));
+    CK(cudaMemsetAsync(d_P, 0, sizeof(S) * (size_t)ldp * nmax, stream));
+    CK(cudaMemsetAsync(d_P2, 0, sizeof(S) * (size_t)ldp * nmax, stream));
+    CK(cudaMemsetAsync(d_poses, 0, sizeof(S) * mb::kPoseStride * (size_t)(Mmax + 1), stream));
+    CK(cudaMemsetAsync(d_poses2, 0, sizeof(S) * mb::kPoseStride * (size_t)(Mmax + 1), stream));
+    const size_t T = Tmax, O = Omax;
+    CK(cudaMalloc(&d_off, sizeof(int) * (T + 1)));
+    CK(cudaMalloc(&d_idx, sizeof(int) * O));
+    for (int** p : {&d_cm, &d_tri, &d_valid, &d_src, &d_accept, &d_rows, &d_scratch}) CK(cudaMalloc(p, sizeof(int) * T));
+    CK(cudaMalloc(&d_rowoff, sizeof(int) * (T + 1)));
+    CK(cudaMalloc(&d_keep, sizeof(int) * nmax));
+    CK(cudaMalloc(&d_m, sizeof(int) * 2));
+    d_rank = d_m + 1;
+    CK(cudaMalloc(&d_keepclones, sizeof(int) * (Mmax + 1)));
+    CK(cudaMalloc(&d_obs, sizeof(S) * 2 * O));
+    CK(cudaMalloc(&d_pfg, sizeof(S) * 3 * T));
+    CK(cudaMalloc(&d_pfg_given, sizeof(S) * 3 * T));
+    CK(cudaMalloc(&d_gamma, sizeof(S) * T));
+    CK(cudaMalloc(&d_Xg, sizeof(S) * 12 * O));
+    CK(cudaMalloc(&d_rg, sizeof(S) * 2 * O));
+    CK(cudaMalloc(&d_Vg, sizeof(S) * 6 * O));
+    CK(cudaMalloc(&d_taug, sizeof(S) * 3 * T));
+    CK(cudaMalloc(&d_Z, sizeof(double) * 3 * T * cmax));
+    CK(cudaMalloc(&d_Yq, sizeof(double) * 3 * T * cmax));
+    CK(cudaMalloc(&d_ur, sizeof(double) * 3 * T));
+    CK(cudaMalloc(&d_G1p, sizeof(double) * kMaxSplit * (size_t)cmax * cmax));
+    CK(cudaMalloc(&d_G2p, sizeof(double) * kMaxSplit * (size_t)cmax * cmax));
+    CK(cudaMalloc(&d_D1, sizeof(double) * 36 * Mmax));
+    CK(cudaMalloc(&d_D2, sizeof(double) * 36 * Mmax));
+    CK(cudaMalloc(&d_bb, sizeof(double) * 6 * Mmax));
+    for (double** p : {&d_T2, &d_R2, &d_TP, &d_S2, &d_W}) CK(cudaMalloc(p, sizeof(double) * (size_t)ld * nmax));
+    CK(cudaMalloc(&d_r2, sizeof(double) * nmax));
+    CK(cudaMalloc(&d_y, sizeof(double) * nmax));
+    CK(cudaMalloc(&d_dx, sizeof(double) * nmax));
+    CK(cudaMemsetAsync(d_dx, 0, sizeof(double) * nmax, stream));
+    CK(cudaMallocHost(&h_off, sizeof(int) * (T + 1)));
+    CK(cudaMallocHost(&h_idx, sizeof(int) * O));
+    CK(cudaMallocHost(&h_flags, sizeof(int) * 4 * T));
+    CK(cudaMallocHost(&h_mr, sizeof(int) * 2));
+    CK(cudaMallocHost(&h_obs, sizeof(S) * 2 * O));
+    CK(cudaMallocHost(&h_pfg_in, sizeof(S) * 3 * T));
+    CK(cudaMallocHost(&h_pfg, sizeof(S) * 3 * T));
+    CK(cudaMallocHost(&h_gamma, sizeof(S) * T));
+    CK(cudaMallocHost(&h_st, sizeof(mb::DevState<S>)));
+    // opt in to large dynamic shared memory
+    CK(cudaFuncSetAttribute(mb::k_tri<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_jac<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_jac<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_jac<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_jac<S, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_head<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  ~Engine() override {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    void* dv[] = {d_st, d_P, d_P2, d_poses, d_poses2, d_off, d_idx, d_cm, d_tri, d_valid, d_src, d_accept, d_rows, d_rowoff,
+                  d_scratch, d_keep, d_m, d_keepclones, d_obs, d_pfg, d_pfg_given, d_gamma, d_Xg, d_rg, d_Vg, d_taug, d_Z, d_Yq,
+                  d_ur, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_T2, d_R2, d_TP, d_S2, d_W, d_r2, d_y, d_dx};
+    for (void* p : dv) if (p) cudaFree(p);
+    void* hv[] = {h_off, h_idx, h_flags, h_mr, h_obs, h_pfg_in, h_pfg, h_gamma, h_st};
+    for (void* p : hv) if (p) cudaFreeHost(p);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  int initialize(const void* cam_, const void* noise_, const void* params_, const void* imu_) override {
+    const S* cam = (const S*)cam_; const S* nz = (const S*)noise_; const S* pr = (const S*)params_; const S* im = (const S*)imu_;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamSynchronize(stream));
+    mb::DevState<S>& s = *h_st;
+    memset(&s, 0, sizeof(s));
+    for (int i = 0; i < 4; ++i) s.q_CI[i] = cam[i];
+    for (int i = 0; i < 3; ++i) s.p_C_I[i] = cam[4 + i];
+    s.u_var = nz[0]; s.v_var = nz[1];
+    for (int i = 0; i < 144; ++i) s.Q_imu[i] = nz[2 + i];
+    s.max_gn_cost_norm = pr[0]; s.translation_threshold = pr[1];
+    for (int i = 0; i < 3; ++i) {
+      s.p_I_G[i] = im[i]; s.v_I_G[i] = im[3 + i]; s.b_g[i] = im[6 + i]; s.b_a[i] = im[9 + i]; s.g[i] = im[12 + i];
+      s.p_I_G_null[i] = im[i]; s.v_I_G_null[i] = im[3 + i];
+    }
+    for (int i = 0; i < 4; ++i) { s.q_IG[i] = im[15 + i]; s.q_IG_null[i] = im[15 + i]; }
+    for (int i = 0; i < 99; ++i) s.chi2[i] = (S)kChi2_005[i];  // msckf.h:91-95
+    CK(cudaMemcpyAsync(d_st, h_st, sizeof(s), cudaMemcpyHostToDevice, stream));
+    // imu_covar_ = initial_imu_covar (msckf.h:86)
+    std::vector<S> P0((size_t)ldp * 15, S(0));
+    for (int i = 0; i < 15; ++i)
+      for (int j = 0; j < 15; ++j) P0[(size_t)i * ldp + j] = nz[146 + 15 * i + j];
+    CK(cudaMemsetAsync(d_P, 0, sizeof(S) * (size_t)ldp * nmax, stream));
+    CK(cudaMemcpyAsync(d_P, P0.data(), sizeof(S) * P0.size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    M = 0;
+    initialized = true;
+    pending_mode = -1;
+    return 0;
+  }
+
+  int propagate(const void* r_) override {
+    if (!initialized) return fail(MSCKF_B200_ERR_STATE, "propagate before initialize");
+    const S* r = (const S*)r_;
+    CK(cudaSetDevice(device));
+    mb::k_propagate<S><<<1, 256, 0, stream>>>(d_st, d_P, ldp, M, r[0], r[1], r[2], r[3], r[4], r[5], r[6]);
+    launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  int augment() override {
+    if (!initialized) return fail(MSCKF_B200_ERR_STATE, "augment before initialize");
+    if (M + 1 > Mmax) return fail(MSCKF_B200_ERR_CAPACITY, "augmentState: clone capacity exceeded");
+    CK(cudaSetDevice(device));
+    mb::k_augment<S><<<1, 256, 0, stream>>>(d_st, d_P, ldp, M, d_poses);
+    launches++;
+    CK(cudaGetLastError());
+    M += 1;
+    return 0;
+  }
+
+  template <int WPB>
+  void launch_jac(const mb::FeatArgs<S>& a, size_t smem) {
+    const int grid = (a.n_tracks + WPB - 1) / WPB;
+    mb::k_jac<S, WPB><<<grid, WPB * 32, smem, stream>>>(a);
+  }
+
+  int update_async(int mode, const msckf_b200_tracks* tr) override {
+    if (!initialized) return fail(MSCKF_B200_ERR_STATE, "update before initialize");
+    if (pending_mode >= 0) return fail(MSCKF_B200_ERR_STATE, "previous update not fetched");
+    const int N = tr->n_tracks;
+    if (N < 0 || N > Tmax) return fail(MSCKF_B200_ERR_CAPACITY, "track batch exceeds max_tracks");
+    CK(cudaSetDevice(device));
+    pending_n = N;
+    pending_mode = mode;
+    if (N == 0) return 0;
+    if (M < 1) return fail(MSCKF_B200_ERR_STATE, "update without clones");
+    const int O = tr->obs_offset[N];
+    if (O > Omax) return fail(MSCKF_B200_ERR_CAPACITY, "track batch exceeds max_obs");
+    int Lmax = 0;
+    for (int t = 0; t < N; ++t) {
+      const int L = tr->obs_offset[t + 1] - tr->obs_offset[t];
+      if (L < 1 || L > 98) return fail(MSCKF_B200_ERR_ARG, "track length must be in [1,98] (chi-square table, msckf.h:91)");
+      if (mode != MSCKF_B200_TRIANGULATE && L < 2) return fail(MSCKF_B200_ERR_ARG, "residualised track needs >= 2 observations");
+      Lmax = std::max(Lmax, L);
+    }
+    for (int o = 0; o < O; ++o)
+      if (tr->clone_index[o] < 0 || tr->clone_index[o] >= M) return fail(MSCKF_B200_ERR_ARG, "clone_index out of range");
+    memcpy(h_off, tr->obs_offset, sizeof(int) * (N + 1));
+    memcpy(h_idx, tr->clone_index, sizeof(int) * O);
+    memcpy(h_obs, tr->obs, sizeof(S) * 2 * (size_t)O);
+    CK(cudaMemcpyAsync(d_off, h_off, sizeof(int) * (N + 1), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_idx, h_idx, sizeof(int) * O, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_obs, h_obs, sizeof(S) * 2 * (size_t)O, cudaMemcpyHostToDevice, stream));
+    if (mode == MSCKF_B200_RESIDUALIZE) {
+      if (!tr->p_f_G) return fail(MSCKF_B200_ERR_ARG, "RESIDUALIZE needs p_f_G");
+      memcpy(h_pfg_in, tr->p_f_G, sizeof(S) * 3 * (size_t)N);
+      CK(cudaMemcpyAsync(d_pfg_given, h_pfg_in, sizeof(S) * 3 * (size_t)N, cudaMemcpyHostToDevice, stream));
+    }
+    const int n = 15 + 6 * M, c = 6 * M;
+    mb::FeatArgs<S> a;
+    a.n_tracks = N; a.M = M; a.Lmax = Lmax; a.ldp = ldp;
+    a.obs_off = d_off; a.obs = d_obs; a.clone_idx = d_idx; a.poses = d_poses; a.P = d_P; a.st = d_st;
+    a.pfg = d_pfg; a.cm_ok = d_cm; a.tri_ok = d_tri; a.valid = d_valid; a.src = d_src;
+    a.pfg_given = (mode == MSCKF_B200_RESIDUALIZE) ? d_pfg_given : nullptr;
+    a.accept = d_accept; a.gamma = d_gamma; a.rows = d_rows; a.Xg = d_Xg; a.rg = d_rg; a.Vg = d_Vg; a.taug = d_taug;
+    a.Z = d_Z; a.Yq = d_Yq; a.ur = d_ur;
+    const size_t pose_bytes = 16 + sizeof(S) * mb::kPoseStride * (size_t)M;
+    if (mode != MSCKF_B200_RESIDUALIZE) {
+      const size_t smem = pose_bytes + sizeof(S) * 4 * 12 * (size_t)Lmax;
+      if (smem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_tri shared memory");
+      mb::k_tri<S, 4><<<(N + 3) / 4, 128, smem, stream>>>(a);
+      launches++;
+    }
+    if (mode != MSCKF_B200_TRIANGULATE) {
+      mb::k_resolve<S><<<1, 1024, 0, stream>>>(a, d_st, mode == MSCKF_B200_RESIDUALIZE ? 1 : 0, d_scratch);
+      launches++;
+      const size_t per_warp = sizeof(S) * mb::jac_warp_smem_elems<S>(Lmax);
+      if (pose_bytes + per_warp > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_jac shared memory");
+      int wpb = (int)std::min<size_t>(8, (kSmemBudget - pose_bytes) / per_warp);
+      wpb = wpb >= 8 ? 8 : wpb >= 4 ? 4 : wpb >= 2 ? 2 : 1;
+      // keep enough CTAs in flight to cover the SMs when the batch is small
+      while (wpb > 1 && (N + wpb - 1) / wpb < 148) wpb >>= 1;
+      const size_t smem = pose_bytes + per_warp * wpb;
+      switch (wpb) {
+        case 8: launch_jac<8>(a, smem); break;
+        case 4: launch_jac<4>(a, smem); break;
+        case 2: launch_jac<2>(a, smem); break;
+        default: launch_jac<1>(a, smem); break;
+      }
+      launches++;
+      mb::k_scan<<<1, 1024, 0, stream>>>(N, d_rows, d_rowoff, d_m);
+      launches++;
+      const double du = (double)h_st->u_var, dv = (double)h_st->v_var;
+      mb::k_blockdiag<S><<<M, 128, 0, stream>>>(N, d_off, d_idx, d_accept, d_Xg, d_rg, du, dv, d_D1, d_D2, d_bb);
+      launches++;
+      const int K = 3 * N;
+      int nsplit = std::max(1, std::min(kMaxSplit, K / 96));
+      int kchunk = (K + nsplit - 1) / nsplit;
+      kchunk = (kchunk + mb::GK - 1) / mb::GK * mb::GK;
+      nsplit = (K + kchunk - 1) / kchunk;
+      const int ntile = (c + mb::GT - 1) / mb::GT;
+      mb::k_gram<<<dim3(ntile * (ntile + 1) / 2, nsplit), 256, 0, stream>>>(d_Z, d_Yq, K, c, kchunk, d_G1p, d_G2p);
+      launches++;
+      const int agrid = std::min(592, (n * n + 255) / 256);
+      mb::k_assemble<<<agrid, 256, 0, stream>>>(n, ld, K, nsplit, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_Z, d_ur, d_T2, d_R2, d_r2);
+      launches++;
+      mb::k_head<S><<<1, 256, sizeof(double) * 18 * 2 * (size_t)Lmax, stream>>>(N, n, ld, d_off, d_idx, d_accept, d_rowoff, d_Xg, d_rg, d_Vg,
+                                                                              d_taug, d_Z, du, dv, d_T2, d_R2, d_r2, Lmax);
+      launches++;
+      const dim3 tg((n + 31) / 32, (n + 31) / 32);
+      mb::k_gemm_tp<S><<<tg, 256, 0, stream>>>(n, ld, d_T2, d_P, ldp, d_TP);
+      mb::k_gemm_s<<<tg, 256, 0, stream>>>(n, ld, d_TP, d_T2, d_R2, d_S2);
+      launches += 2;
+      const size_t chol_smem = sizeof(double) * (((n + 1) & ~1) + 32 * 33 + (size_t)n * 33);
+      if (chol_smem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_chol shared memory");
+      mb::k_chol<<<1, 1024, chol_smem, stream>>>(n, ld, d_S2, d_keep, rank_thr, d_rank);
+      launches++;
+      const size_t trsm_smem = sizeof(double) * ((size_t)n * 33 + 32 * 33);
+      mb::k_trsm<<<(n + 1 + 31) / 32, 256, trsm_smem, stream>>>(n, ld, d_S2, d_keep, d_TP, d_r2, d_W, d_y);
+      launches++;
+      mb::k_syrk_apply<S><<<tg, 256, 0, stream>>>(n, ld, d_W, d_P, ldp);
+      launches++;
+      mb::k_inject<S><<<1, 256, sizeof(double) * n, stream>>>(n, ld, M, d_W, d_y, d_st, d_poses, d_dx, d_m, d_rank);
+      launches++;
+    }
+    CK(cudaGetLastError());
+    // report back (pinned), still asynchronous
+    if (mode != MSCKF_B200_RESIDUALIZE) {
+      CK(cudaMemcpyAsync(h_flags, d_cm, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(h_flags + Tmax, d_tri, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(h_pfg, d_pfg, sizeof(S) * 3 * (size_t)N, cudaMemcpyDeviceToHost, stream));
+    }
+    if (mode != MSCKF_B200_TRIANGULATE) {
+      CK(cudaMemcpyAsync(h_flags + 2 * (size_t)Tmax, d_valid, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(h_flags + 3 * (size_t)Tmax, d_accept, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(h_gamma, d_gamma, sizeof(S) * N, cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(h_mr, d_m, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream));
+    }
+    return 0;
+  }
+
+  int fetch(msckf_b200_report* rep) override {
+    if (pending_mode < 0) return fail(MSCKF_B200_ERR_STATE, "fetch without a pending update");
+    CK(cudaSetDevice(device));
+    CK(cudaStreamSynchronize(stream));
+    const int N = pending_n, mode = pending_mode;
+    pending_mode = -1;
+    if (!rep) return 0;
+    rep->m = 0; rep->rank = 0;
+    if (N == 0) return 0;
+    if (mode != MSCKF_B200_RESIDUALIZE) {
+      if (rep->cm_ok) memcpy(rep->cm_ok, h_flags, sizeof(int) * N);
+      if (rep->tri_ok) memcpy(rep->tri_ok, h_flags + Tmax, sizeof(int) * N);
+      if (rep->p_f_G) memcpy(rep->p_f_G, h_pfg, sizeof(S) * 3 * (size_t)N);
+    }
+    if (mode != MSCKF_B200_TRIANGULATE) {
+      if (rep->valid) memcpy(rep->valid, h_flags + 2 * (size_t)Tmax, sizeof(int) * N);
+      if (rep->accepted) memcpy(rep->accepted, h_flags + 3 * (size_t)Tmax, sizeof(int) * N);
+      if (rep->gamma) memcpy(rep->gamma, h_gamma, sizeof(S) * N);
+      rep->m = h_mr[0];
+      rep->rank = h_mr[1];
+    }
+    return 0;
+  }
+
+  int prune(const int* keep, int n_keep) override {
+    if (n_keep < 0 || n_keep > M) return fail(MSCKF_B200_ERR_ARG, "prune: bad keep count");
+    for (int i = 0; i < n_keep; ++i)
+      if (keep[i] < 0 || keep[i] >= M || (i && keep[i] <= keep[i - 1])) return fail(MSCKF_B200_ERR_ARG, "prune: keep[] must be ascending positions");
+    if (n_keep == M) return 0;
+    CK(cudaSetDevice(device));
+    CK(cudaMemcpyAsync(d_keepclones, keep, sizeof(int) * std::max(n_keep, 1), cudaMemcpyHostToDevice, stream));
+    const int n_new = 15 + 6 * n_keep;
+    mb::k_gather<S><<<std::min(296, (n_new * n_new + 255) / 256), 256, 0, stream>>>(n_new, d_keepclones, n_keep, d_P, d_P2, ldp, d_poses, d_poses2);
+    launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(stream));  // keep[] is caller memory
+    std::swap(d_P, d_P2);
+    std::swap(d_poses, d_poses2);
+    M = n_keep;
+    return 0;
+  }
+
+  int get_state(void* imu_, void* poses_) override {
+    CK(cudaSetDevice(device));
+    if (imu_) {
+      CK(cudaMemcpyAsync(h_st, d_st, sizeof(mb::DevState<S>), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      S* o = (S*)imu_;
+      const mb::DevState<S>& s = *h_st;
+      for (int i = 0; i < 3; ++i) {
+        o[i] = s.p_I_G[i]; o[3 + i] = s.v_I_G[i]; o[6 + i] = s.b_g[i]; o[9 + i] = s.b_a[i]; o[12 + i] = s.g[i];
+        o[19 + i] = s.p_I_G_null[i]; o[22 + i] = s.v_I_G_null[i];
+      }
+      for (int i = 0; i < 4; ++i) { o[15 + i] = s.q_IG[i]; o[25 + i] = s.q_IG_null[i]; }
+    }
+    if (poses_ && M > 0) {
+      std::vector<S> tmp((size_t)mb::kPoseStride * M);
+      CK(cudaMemcpyAsync(tmp.data(), d_poses, sizeof(S) * tmp.size(), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      S* o = (S*)poses_;
+      for (int k = 0; k < M; ++k) {
+        const S* p = tmp.data() + mb::kPoseStride * k;
+        o[7 * k] = p[4]; o[7 * k + 1] = p[5]; o[7 * k + 2] = p[6];
+        o[7 * k + 3] = p[0]; o[7 * k + 4] = p[1]; o[7 * k + 5] = p[2]; o[7 * k + 6] = p[3];
+      }
+    }
+    return 0;
+  }
+
+  int get_covariance(void* out) override {
+    CK(cudaSetDevice(device));
+    const int n = 15 + 6 * M;
+    CK(cudaMemcpy2DAsync(out, sizeof(S) * n, d_P, sizeof(S) * ldp, sizeof(S) * n, n, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return n;
+  }
+
+  int get_counters(long long* c) override {
+    CK(cudaSetDevice(device));
+    CK(cudaMemcpyAsync(h_st, d_st, sizeof(mb::DevState<S>), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    c[0] = (long long)h_st->num_residualized; c[1] = (long long)h_st->pfg_shifted; c[2] = (long long)h_st->pfg_oob;
+    c[3] = (long long)h_st->n_updates; c[4] = h_st->last_m; c[5] = h_st->last_rank; c[6] = 0; c[7] = 0;
+    return 0;
+  }
+
+  int last_dx(double* out, int cap) override {
+    CK(cudaSetDevice(device));
+    const int n = 15 + 6 * M;
+    std::vector<double> tmp(n);
+    CK(cudaMemcpyAsync(tmp.data(), d_dx, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int i = 0; i < std::min(n, cap); ++i) out[i] = tmp[i];
+    return n;
+  }
+
+  int copy_from(const EngineBase* src_) override {
+    const Engine<S>* src = dynamic_cast<const Engine<S>*>(src_);
+    if (!src || src->Mmax != Mmax || src->device != device) return fail(MSCKF_B200_ERR_ARG, "copy_state: incompatible engines");
+    CK(cudaSetDevice(device));
+    CK(cudaStreamSynchronize(src->stream));
+    CK(cudaMemcpyAsync(d_st, src->d_st, sizeof(mb::DevState<S>), cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpyAsync(d_P, src->d_P, sizeof(S) * (size_t)ldp * nmax, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpyAsync(d_poses, src->d_poses, sizeof(S) * mb::kPoseStride * (size_t)(Mmax + 1), cudaMemcpyDeviceToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    memcpy(h_st, src->h_st, sizeof(mb::DevState<S>));
+    M = src->M;
+    initialized = src->initialized;
+    rank_thr = src->rank_thr;
+    pending_mode = -1;
+    return 0;
+  }
+
+  int sync() override {
+    CK(cudaSetDevice(device));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+};
+}  // namespace
+
+struct msckf_b200_engine { EngineBase* impl; };
+
+extern "C" {
+const char* msckf_b200_last_error(void) { return g_err.c_str(); }
+
+int msckf_b200_create(const msckf_b200_config* cfg, msckf_b200_engine** out) {
+  if (!cfg || !out) return fail(MSCKF_B200_ERR_ARG, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(MSCKF_B200_ERR_NO_DEVICE, "no CUDA device: the B200 engine has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(MSCKF_B200_ERR_ARG, "bad device ordinal");
+  if (cfg->max_clones < 1 || cfg->max_tracks < 1 || cfg->max_obs < 1) return fail(MSCKF_B200_ERR_ARG, "bad capacities");
+  EngineBase* b = nullptr;
+  if (cfg->dtype == MSCKF_B200_F32) b = new Engine<float>();
+  else if (cfg->dtype == MSCKF_B200_F64) b = new Engine<double>();
+  else return fail(MSCKF_B200_ERR_ARG, "bad dtype");
+  b->dtype = cfg->dtype; b->device = cfg->device; b->Mmax = cfg->max_clones; b->Tmax = cfg->max_tracks; b->Omax = cfg->max_obs;
+  int rc = (cfg->dtype == MSCKF_B200_F32) ? static_cast<Engine<float>*>(b)->alloc() : static_cast<Engine<double>*>(b)->alloc();
+  if (rc != 0) { delete b; return rc; }
+  *out = new msckf_b200_engine{b};
+  return 0;
+}
+int msckf_b200_destroy(msckf_b200_engine* e) {
+  if (!e) return 0;
+  delete e->impl;
+  delete e;
+  return 0;
+}
+int msckf_b200_initialize(msckf_b200_engine* e, const void* camera, const void* noise, const void* params, const void* imu_state) {
+  return e->impl->initialize(camera, noise, params, imu_state);
+}
+int msckf_b200_propagate(msckf_b200_engine* e, const void* reading) { return e->impl->propagate(reading); }
+int msckf_b200_augment(msckf_b200_engine* e) { return e->impl->augment(); }
+int msckf_b200_update_async(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks) { return e->impl->update_async(mode, tracks); }
+int msckf_b200_fetch(msckf_b200_engine* e, msckf_b200_report* report) { return e->impl->fetch(report); }
+int msckf_b200_update(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks, msckf_b200_report* report) {
+  int rc = e->impl->update_async(mode, tracks);
+  if (rc != 0) { e->impl->fetch(nullptr); return rc; }
+  return e->impl->fetch(report);
+}
+int msckf_b200_prune(msckf_b200_engine* e, const int* keep, int n_keep) { return e->impl->prune(keep, n_keep); }
+int msckf_b200_num_clones(msckf_b200_engine* e) { return e->impl->M; }
+int msckf_b200_get_state(msckf_b200_engine* e, void* imu, void* clone_poses) { return e->impl->get_state(imu, clone_poses); }
+int msckf_b200_get_covariance(msckf_b200_engine* e, void* out) { return e->impl->get_covariance(out); }
+int msckf_b200_get_counters(msckf_b200_engine* e, long long* counters) { return e->impl->get_counters(counters); }
+int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap) { return e->impl->last_dx(out, cap); }
+int msckf_b200_set_option(msckf_b200_engine* e, int key, double value) {
+  if (key == 0) { e->impl->rank_thr = value; return 0; }
+  return fail(MSCKF_B200_ERR_ARG, "unknown option");
+}
+int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src) { return dst->impl->copy_from(src->impl); }
+long long msckf_b200_launch_count(const msckf_b200_engine* e) { return e->impl->launches; }
+void* msckf_b200_stream(msckf_b200_engine* e) { return (void*)e->impl->stream; }
+int msckf_b200_synchronize(msckf_b200_engine* e) { return e->impl->sync(); }
+}

@@ -58,7 +58,14 @@ class CFilter:
 
     def _chk(self, rc, what):
         if rc < 0:
-            raise RuntimeError(f"{self.prefix}{what} failed rc={rc}")
+            msg = ""
+            try:
+                fn = getattr(self.lib, self.prefix + "last_error")
+                fn.restype = C.c_char_p
+                msg = (fn() or b"").decode()
+            except AttributeError:
+                pass
+            raise RuntimeError(f"{self.prefix}{what} failed rc={rc} {msg}")
         return rc
 
     def close(self):

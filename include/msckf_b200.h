@@ -84,6 +84,14 @@ int msckf_b200_augment(msckf_b200_engine* e);
  * copied to pinned staging before return; results are fetched (and the stream synchronised) by _fetch. */
 int msckf_b200_update_async(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks);
 int msckf_b200_fetch(msckf_b200_engine* e, msckf_b200_report* report);
+/* update_async split in two: _stage validates and copies the batch into HBM, _launch enqueues the kernels
+ * (bench.py times _launch alone: "inputs already resident in HBM") */
+int msckf_b200_stage(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks);
+int msckf_b200_launch(msckf_b200_engine* e);
+/* _launch bracketed by CUDA events on the handle's stream (kernels only); *ms = device time */
+int msckf_b200_launch_timed(msckf_b200_engine* e, float* ms);
+/* with option key 1 set, per-kernel device times of the last launch (launch order); returns the count */
+int msckf_b200_kernel_times(msckf_b200_engine* e, float* ms, const char** names, int cap);
 /* update_async + fetch */
 int msckf_b200_update(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks, msckf_b200_report* report);
 /* covariance / pose gather of pruneEmptyStates msckf.h:685-761 and pruneRedundantStates :616-681:
@@ -99,7 +107,8 @@ int msckf_b200_get_covariance(msckf_b200_engine* e, void* out);
 int msckf_b200_get_counters(msckf_b200_engine* e, long long* counters);
 /* last delta-x (fp64), returns its length */
 int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap);
-/* option keys: 0 = rank threshold of the compression (relative pivot, default 1e-10) */
+/* option keys: 0 = rank threshold of the compression (relative pivot of the basis Gram matrix = squared sine to the span of the previous basis vectors, default 1e-11);
+ *              1 = record per-kernel CUDA events in _launch (profiling aid, default off) */
 int msckf_b200_set_option(msckf_b200_engine* e, int key, double value);
 /* checkpoint / resume: copy the complete filter state of src into dst (same dtype and capacities) */
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src);

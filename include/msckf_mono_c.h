@@ -42,6 +42,8 @@ int msckf_mono_get_counters(void* h, long* out8);
 int msckf_mono_set_option(void* h, int key, double value);
 int msckf_mono_last_delta_x(void* h, double* out, int cap);
 int msckf_mono_queued_tracks(void* h, uint64_t* ids, int* nobs, int cap);
+/* the track batch queued by update()/finish() in the engine's flat SoA form (obs as double); returns n_tracks */
+int msckf_mono_pack_queued(void* h, int* obs_offset, double* obs, int* clone_index, int cap_tracks, int cap_obs);
 /* pipelining helpers: marginalize() = launch + collect */
 int msckf_mono_marginalize_launch(void* h);
 int msckf_mono_marginalize_collect(void* h);

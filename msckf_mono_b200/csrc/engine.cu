@@ -46,9 +46,14 @@ struct EngineBase {
   virtual int last_dx(double*, int) = 0;
   virtual int copy_from(const EngineBase*) = 0;
   virtual int sync() = 0;
+  virtual int stage(int mode, const msckf_b200_tracks*) = 0;
+  virtual int launch() = 0;
+  virtual int launch_timed(float* ms) = 0;
+  virtual int kernel_times(float* ms, const char** names, int cap) = 0;
+  bool profile = false;
   int dtype = 0, device = 0, Mmax = 0, Tmax = 0, Omax = 0;
   int M = 0;
-  double rank_thr = 1e-10;
+  double rank_thr = 1e-11;
   long long launches = 0;
   cudaStream_t stream = nullptr;
 };
@@ -73,6 +78,23 @@ struct Engine : EngineBase {
   int nmax = 0, ldp = 0, ld = 0;
   int pending_n = 0, pending_mode = -1;
   bool initialized = false;
+  // staged batch
+  int st_N = 0, st_O = 0, st_Lmax = 0, st_mode = -1;
+  bool staged = false;
+  bool timed_region = false;
+  // optional per-kernel CUDA-event profile of the last launch (option key 1)
+  static constexpr int kMaxEv = 24;
+  cudaEvent_t ev[kMaxEv] = {};
+  const char* ev_name[kMaxEv] = {};
+  int n_ev = 0;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  void mark(const char* name) {
+    if (!profile || n_ev >= kMaxEv) return;
+    if (!ev[n_ev]) cudaEventCreate(&ev[n_ev]);
+    cudaEventRecord(ev[n_ev], stream);
+    ev_name[n_ev] = name;
+    n_ev++;
+  }
 
   int alloc() {
     nmax = 15 + 6 * Mmax;
@@ -137,7 +159,6 @@ struct Engine : EngineBase {
     CK(cudaFuncSetAttribute(mb::k_jac<S, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_head<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaStreamSynchronize(stream));
     return 0;
   }
@@ -212,14 +233,21 @@ struct Engine : EngineBase {
   }
 
   int update_async(int mode, const msckf_b200_tracks* tr) override {
+    int rc = stage(mode, tr);
+    if (rc != 0) return rc;
+    return launch();
+  }
+
+  // validate + copy the batch to the device (pinned staging, asynchronous)
+  int stage(int mode, const msckf_b200_tracks* tr) override {
     if (!initialized) return fail(MSCKF_B200_ERR_STATE, "update before initialize");
     if (pending_mode >= 0) return fail(MSCKF_B200_ERR_STATE, "previous update not fetched");
     const int N = tr->n_tracks;
     if (N < 0 || N > Tmax) return fail(MSCKF_B200_ERR_CAPACITY, "track batch exceeds max_tracks");
     CK(cudaSetDevice(device));
-    pending_n = N;
-    pending_mode = mode;
-    if (N == 0) return 0;
+    staged = false;
+    st_N = N; st_mode = mode; st_O = 0; st_Lmax = 0;
+    if (N == 0) { staged = true; return 0; }
     if (M < 1) return fail(MSCKF_B200_ERR_STATE, "update without clones");
     const int O = tr->obs_offset[N];
     if (O > Omax) return fail(MSCKF_B200_ERR_CAPACITY, "track batch exceeds max_obs");
@@ -243,6 +271,22 @@ struct Engine : EngineBase {
       memcpy(h_pfg_in, tr->p_f_G, sizeof(S) * 3 * (size_t)N);
       CK(cudaMemcpyAsync(d_pfg_given, h_pfg_in, sizeof(S) * 3 * (size_t)N, cudaMemcpyHostToDevice, stream));
     }
+    st_O = O; st_Lmax = Lmax;
+    staged = true;
+    return 0;
+  }
+
+  // launch the kernels of the staged batch and queue the report copies (all asynchronous)
+  int launch() override {
+    if (!staged) return fail(MSCKF_B200_ERR_STATE, "launch without a staged batch");
+    staged = false;
+    const int N = st_N, mode = st_mode, Lmax = st_Lmax;
+    CK(cudaSetDevice(device));
+    pending_n = N;
+    pending_mode = mode;
+    n_ev = 0;
+    if (N == 0) return 0;
+    mark("begin");
     const int n = 15 + 6 * M, c = 6 * M;
     mb::FeatArgs<S> a;
     a.n_tracks = N; a.M = M; a.Lmax = Lmax; a.ldp = ldp;
@@ -257,10 +301,12 @@ struct Engine : EngineBase {
       if (smem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_tri shared memory");
       mb::k_tri<S, 4><<<(N + 3) / 4, 128, smem, stream>>>(a);
       launches++;
+      mark("k_tri");
     }
     if (mode != MSCKF_B200_TRIANGULATE) {
       mb::k_resolve<S><<<1, 1024, 0, stream>>>(a, d_st, mode == MSCKF_B200_RESIDUALIZE ? 1 : 0, d_scratch);
       launches++;
+      mark("k_resolve");
       const size_t per_warp = sizeof(S) * mb::jac_warp_smem_elems<S>(Lmax);
       if (pose_bytes + per_warp > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_jac shared memory");
       int wpb = (int)std::min<size_t>(8, (kSmemBudget - pose_bytes) / per_warp);
@@ -275,11 +321,14 @@ struct Engine : EngineBase {
         default: launch_jac<1>(a, smem); break;
       }
       launches++;
+      mark("k_jac");
       mb::k_scan<<<1, 1024, 0, stream>>>(N, d_rows, d_rowoff, d_m);
       launches++;
+      mark("k_scan");
       const double du = (double)h_st->u_var, dv = (double)h_st->v_var;
       mb::k_blockdiag<S><<<M, 128, 0, stream>>>(N, d_off, d_idx, d_accept, d_Xg, d_rg, du, dv, d_D1, d_D2, d_bb);
       launches++;
+      mark("k_blockdiag");
       const int K = 3 * N;
       int nsplit = std::max(1, std::min(kMaxSplit, K / 96));
       int kchunk = (K + nsplit - 1) / nsplit;
@@ -288,29 +337,45 @@ struct Engine : EngineBase {
       const int ntile = (c + mb::GT - 1) / mb::GT;
       mb::k_gram<<<dim3(ntile * (ntile + 1) / 2, nsplit), 256, 0, stream>>>(d_Z, d_Yq, K, c, kchunk, d_G1p, d_G2p);
       launches++;
+      mark("k_gram");
       const int agrid = std::min(592, (n * n + 255) / 256);
-      mb::k_assemble<<<agrid, 256, 0, stream>>>(n, ld, K, nsplit, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_Z, d_ur, d_T2, d_R2, d_r2);
+      mb::k_assemble<<<agrid, 256, 0, stream>>>(n, ld, K, nsplit, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_Z, d_ur, d_m, d_T2, d_R2, d_r2);
       launches++;
-      mb::k_head<S><<<1, 256, sizeof(double) * 18 * 2 * (size_t)Lmax, stream>>>(N, n, ld, d_off, d_idx, d_accept, d_rowoff, d_Xg, d_rg, d_Vg,
-                                                                              d_taug, d_Z, du, dv, d_T2, d_R2, d_r2, Lmax);
+      mark("k_assemble");
+      mb::k_rows<S><<<N, 128, sizeof(double) * 12 * (size_t)Lmax, stream>>>(N, n, ld, d_off, d_idx, d_accept, d_rowoff, d_m, d_Xg, d_rg, d_Vg,
+                                                                            d_taug, d_Z, du, dv, d_T2, d_R2, d_r2);
       launches++;
+      mark("k_rows");
       const dim3 tg((n + 31) / 32, (n + 31) / 32);
       mb::k_gemm_tp<S><<<tg, 256, 0, stream>>>(n, ld, d_T2, d_P, ldp, d_TP);
+      mark("k_gemm_tp");
       mb::k_gemm_s<<<tg, 256, 0, stream>>>(n, ld, d_TP, d_T2, d_R2, d_S2);
+      mark("k_gemm_s");
       launches += 2;
-      const size_t chol_smem = sizeof(double) * (((n + 1) & ~1) + 32 * 33 + (size_t)n * 33);
+      const size_t chol_smem = sizeof(double) * (((n + 1) & ~1) + 32 * 33 + (size_t)n * 33) + sizeof(int) * n;
       if (chol_smem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_chol shared memory");
-      mb::k_chol<<<1, 1024, chol_smem, stream>>>(n, ld, d_S2, d_keep, rank_thr, d_rank);
+      // rank decision on the basis Gram matrix (d_W is free until k_trsm), then the factorisation of S''
+      mb::k_gamma<<<agrid, 256, 0, stream>>>(n, ld, d_T2, d_m, d_W);
+      mb::k_chol<<<1, 1024, chol_smem, stream>>>(n, ld, d_W, d_keep, rank_thr, d_rank, d_m, 1);
+      launches += 2;
+      mark("k_rank");
+      mb::k_chol<<<1, 1024, chol_smem, stream>>>(n, ld, d_S2, d_keep, rank_thr, d_rank, d_m, 0);
       launches++;
-      const size_t trsm_smem = sizeof(double) * ((size_t)n * 33 + 32 * 33);
+      mark("k_chol");
+      const size_t trsm_smem = sizeof(double) * (2 * (size_t)n * 33 + 32 * 33) + sizeof(int) * n;
+      if (trsm_smem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_trsm shared memory");
       mb::k_trsm<<<(n + 1 + 31) / 32, 256, trsm_smem, stream>>>(n, ld, d_S2, d_keep, d_TP, d_r2, d_W, d_y);
       launches++;
+      mark("k_trsm");
       mb::k_syrk_apply<S><<<tg, 256, 0, stream>>>(n, ld, d_W, d_P, ldp);
       launches++;
+      mark("k_syrk_apply");
       mb::k_inject<S><<<1, 256, sizeof(double) * n, stream>>>(n, ld, M, d_W, d_y, d_st, d_poses, d_dx, d_m, d_rank);
       launches++;
+      mark("k_inject");
     }
     CK(cudaGetLastError());
+    if (timed_region) CK(cudaEventRecord(ev_t1, stream));
     // report back (pinned), still asynchronous
     if (mode != MSCKF_B200_RESIDUALIZE) {
       CK(cudaMemcpyAsync(h_flags, d_cm, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
@@ -444,6 +509,33 @@ struct Engine : EngineBase {
     CK(cudaStreamSynchronize(stream));
     return 0;
   }
+
+  // launch() bracketed by CUDA events on this handle's stream; the staged inputs are already in HBM.
+  // The report copies are queued after the stop event, so the time is kernels only.
+  int launch_timed(float* ms) override {
+    CK(cudaSetDevice(device));
+    if (!ev_t0) { CK(cudaEventCreate(&ev_t0)); CK(cudaEventCreate(&ev_t1)); }
+    CK(cudaStreamSynchronize(stream));
+    timed_region = true;
+    CK(cudaEventRecord(ev_t0, stream));
+    int rc = launch();
+    timed_region = false;
+    if (rc != 0) return rc;
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaEventElapsedTime(ms, ev_t0, ev_t1));
+    return 0;
+  }
+
+  int kernel_times(float* ms, const char** names, int cap) override {
+    CK(cudaSetDevice(device));
+    CK(cudaStreamSynchronize(stream));
+    int k = 0;
+    for (int i = 1; i < n_ev && k < cap; ++i, ++k) {
+      CK(cudaEventElapsedTime(&ms[k], ev[i - 1], ev[i]));
+      names[k] = ev_name[i];
+    }
+    return k;
+  }
 };
 }  // namespace
 
@@ -493,8 +585,13 @@ int msckf_b200_get_state(msckf_b200_engine* e, void* imu, void* clone_poses) { r
 int msckf_b200_get_covariance(msckf_b200_engine* e, void* out) { return e->impl->get_covariance(out); }
 int msckf_b200_get_counters(msckf_b200_engine* e, long long* counters) { return e->impl->get_counters(counters); }
 int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap) { return e->impl->last_dx(out, cap); }
+int msckf_b200_stage(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks) { return e->impl->stage(mode, tracks); }
+int msckf_b200_launch(msckf_b200_engine* e) { return e->impl->launch(); }
+int msckf_b200_launch_timed(msckf_b200_engine* e, float* ms) { return e->impl->launch_timed(ms); }
+int msckf_b200_kernel_times(msckf_b200_engine* e, float* ms, const char** names, int cap) { return e->impl->kernel_times(ms, names, cap); }
 int msckf_b200_set_option(msckf_b200_engine* e, int key, double value) {
   if (key == 0) { e->impl->rank_thr = value; return 0; }
+  if (key == 1) { e->impl->profile = value != 0; return 0; }
   return fail(MSCKF_B200_ERR_ARG, "unknown option");
 }
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src) { return dst->impl->copy_from(src->impl); }

@@ -270,6 +270,7 @@ __global__ void k_resolve(FeatArgs<S> a, DevState<S>* st, int mode, int* pushed_
     int k = 0;
     for (; k < N && counter <= 3; ++k) {
       pushed_scratch[k] = 1;  // checkMotion not consulted -> initializePosition ran -> p_f_G pushed
+      a.cm_ok[k] = 1;         // report: "not rejected by checkMotion" (msckf.h:354)
       const int v = a.tri_ok[k];
       a.valid[k] = v;
       if (v) counter++;
@@ -341,8 +342,8 @@ __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; } 
 
 template <class S>
 __host__ __device__ inline size_t jac_warp_smem_elems(int L) {
-  // X 12L | r 2L | V 6L | U 6L | w 2L | p 2L | Ypacked L(2L+1)
-  return (size_t)30 * L + (size_t)L * (2 * L + 1);
+  // X 12L | r 2L | V 6L | U64 6L doubles (= 12L floats worst case) | w 2L | p 2L | Ypacked L(2L+1)
+  return (size_t)36 * L + (size_t)L * (2 * L + 1) + 4;
 }
 
 template <class S, int WPB>
@@ -366,11 +367,13 @@ __global__ void __launch_bounds__(WPB * 32) k_jac(FeatArgs<S> a) {
   }
   const int* idx = a.clone_idx + o0;
   const S* z = a.obs + 2 * (size_t)o0;
-  S* X = ws_all + (size_t)warp * jac_warp_smem_elems<S>(a.Lmax);
+  S* wbase = ws_all + (size_t)warp * jac_warp_smem_elems<S>(a.Lmax);
+  // U in fp64 (8-byte aligned: the per-warp region starts 16-byte aligned and its size is even in S units)
+  double* U = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(wbase) + 7) & ~uintptr_t(7));
+  S* X = reinterpret_cast<S*>(U + 3 * L2);
   S* r = X + 12 * L;
   S* V = r + L2;
-  S* U = V + 3 * L2;
-  S* wv = U + 3 * L2;
+  S* wv = V + 3 * L2;
   S* pv = wv + L2;
   S* Y = pv + L2;
   const DevState<S>* st = a.st;
@@ -481,26 +484,45 @@ __global__ void __launch_bounds__(WPB * 32) k_jac(FeatArgs<S> a) {
   // export v_k, tau for the head-row kernel
   for (int e = lane; e < 3 * L2; e += 32) a.Vg[3 * 2 * (size_t)o0 + e] = V[e];
   if (lane < 3) a.taug[3 * t + lane] = tau[lane];
-  // ---- r~ = H3 H2 H1 r  (r_o = r~[3:], U^T r = r~[0:3])
+  // ---- exact reflectors for the Gram stage: H_k = I - tau64_k v_k v_k^T with tau64_k = 2 / (v_k^T v_k) evaluated in
+  // fp64 from the stored vectors.  Q = H_0 H_1 H_2 is then orthogonal to 1e-16 whatever the filter precision, so
+  // G_j = I - U_j U_j^T is an exact projector and the body Gram terms and the head rows (k_head) describe the same H_o.
+  double tau64[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double sacc = 0.0;
+    for (int row = k + lane; row < L2; row += 32) { const double vv = (double)V[3 * row + k]; sacc += vv * vv; }
+    const double vtv = warp_sum(sacc);
+    tau64[k] = (tau[k] != S(0)) ? 2.0 / vtv : 0.0;
+  }
+  // ---- U = Q(:,0:3) = H0 H1 H2 [I3; 0]  (fp64)
+  for (int e = lane; e < 3 * L2; e += 32) U[e] = ((e / 3) == (e % 3)) ? 1.0 : 0.0;
+  __syncwarp();
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    for (int cc = 0; cc < 3; ++cc) {
+      double sacc = 0.0;
+      for (int row = k + lane; row < L2; row += 32) sacc += (double)V[3 * row + k] * U[3 * row + cc];
+      const double sdot = tau64[k] * warp_sum(sacc);
+      for (int row = k + lane; row < L2; row += 32) U[3 * row + cc] -= sdot * (double)V[3 * row + k];
+    }
+    __syncwarp();
+  }
+  // U^T r in fp64 from the raw residual
+  double urv[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double sacc = 0.0;
+    for (int row = lane; row < L2; row += 32) sacc += U[3 * row + q] * (double)r[row];
+    urv[q] = warp_sum(sacc);
+  }
+  // ---- r~ = H2 H1 H0 r in the filter precision (r_o = r~[3:], used by the gate only)
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     S sacc = 0;
     for (int row = k + lane; row < L2; row += 32) sacc += V[3 * row + k] * r[row];
     const S sdot = tau[k] * warp_sum(sacc);
     for (int row = k + lane; row < L2; row += 32) r[row] -= sdot * V[3 * row + k];
-    __syncwarp();
-  }
-  // ---- U = Q(:,0:3) = H1 H2 H3 [I3; 0]
-  for (int e = lane; e < 3 * L2; e += 32) U[e] = ((e / 3) == (e % 3)) ? S(1) : S(0);
-  __syncwarp();
-#pragma unroll
-  for (int k = 2; k >= 0; --k) {
-    for (int cc = 0; cc < 3; ++cc) {
-      S sacc = 0;
-      for (int row = k + lane; row < L2; row += 32) sacc += V[3 * row + k] * U[3 * row + cc];
-      const S sdot = tau[k] * warp_sum(sacc);
-      for (int row = k + lane; row < L2; row += 32) U[3 * row + cc] -= sdot * V[3 * row + k];
-    }
     __syncwarp();
   }
   // ---- gating (msckf.h:1103-1124): gamma = r_o^T (H_o P H_o^T + u_var I)^-1 r_o with H_o = (Q^T X)[3:]
@@ -594,7 +616,6 @@ __global__ void __launch_bounds__(WPB * 32) k_jac(FeatArgs<S> a) {
   S gam = warp_sum(gacc);
   const int acc = chol_ok && (gam < st->chi2[L]);  // table[dof+1], dof = L-1 (msckf.h:433,:1117)
   if (!chol_ok) gam = S(1e30);
-  // NB: r[0:3] still holds U^T r (rows < 3 are untouched by the Cholesky loop)
   // ---- compact outputs for the Gram stage
   for (int k = lane; k < 3 * c; k += 32) { Zr[k] = 0.0; Yr[k] = 0.0; }
   // M = U^T D U (3x3 symmetric), D = diag(u_var, v_var, u_var, ...)
@@ -637,7 +658,7 @@ __global__ void __launch_bounds__(WPB * 32) k_jac(FeatArgs<S> a) {
     a.accept[t] = acc;
     a.gamma[t] = gam;
     a.rows[t] = acc ? (L2 - 3) : 0;
-    for (int q = 0; q < 3; ++q) a.ur[3 * t + q] = acc ? (double)r[q] : 0.0;
+    for (int q = 0; q < 3; ++q) a.ur[3 * t + q] = acc ? urv[q] : 0.0;
   }
 }
 

@@ -33,6 +33,7 @@ struct Base {
   virtual int tracked_ids(uint64_t*, int) = 0;
   virtual int report(int*, double*, double*, int) = 0;
   virtual int queued(uint64_t*, int*, int) = 0;
+  virtual int pack_queued(int*, double*, int*, int, int) = 0;
   virtual msckf_b200_engine* engine() = 0;
   virtual int last_m() = 0;
   virtual int last_rank() = 0;
@@ -150,6 +151,22 @@ struct Impl : Base {
     for (int i = 0; i < std::min((int)q.size(), cap); ++i) { ids[i] = q[i].feature_id; nobs[i] = (int)q[i].observations.size(); }
     return (int)q.size();
   }
+  int pack_queued(int* off, double* obs, int* idx, int cap_tracks, int cap_obs) override {
+    const auto& q = f.tracksToResidualize();
+    int tot = 0;
+    if ((int)q.size() > cap_tracks) return -2;
+    for (size_t t = 0; t < q.size(); ++t) {
+      off[t] = tot;
+      for (size_t i = 0; i < q[t].observations.size(); ++i) {
+        if (tot >= cap_obs) return -2;
+        obs[2 * tot] = q[t].observations[i](0); obs[2 * tot + 1] = q[t].observations[i](1);
+        idx[tot] = (int)q[t].cam_state_indices[i];
+        ++tot;
+      }
+    }
+    off[q.size()] = tot;
+    return (int)q.size();
+  }
   msckf_b200_engine* engine() override { return f.engine(); }
   int last_m() override { return f.lastStackedRows(); }
   int last_rank() override { return f.lastRank(); }
@@ -217,6 +234,7 @@ int msckf_mono_set_option(void* h, int key, double v) {
 }
 int msckf_mono_last_delta_x(void* h, double* out, int cap) { return guard([&] { return msckf_b200_last_delta_x(H->engine(), out, cap); }); }
 int msckf_mono_queued_tracks(void* h, uint64_t* ids, int* nobs, int cap) { return guard([&] { return H->queued(ids, nobs, cap); }); }
+int msckf_mono_pack_queued(void* h, int* off, double* obs, int* idx, int cap_tracks, int cap_obs) { return guard([&] { return H->pack_queued(off, obs, idx, cap_tracks, cap_obs); }); }
 void* msckf_mono_engine(void* h) { return H->engine(); }
 int msckf_mono_clone_from(void* dst, void* src) {
   (void)dst; (void)src;

@@ -121,14 +121,15 @@ __global__ void __launch_bounds__(128) k_blockdiag(int N, const int* __restrict_
 __global__ void __launch_bounds__(256) k_assemble(int n, int ld, int K, int nsplit, const double* __restrict__ G1p,
                                                  const double* __restrict__ G2p, const double* __restrict__ D1,
                                                  const double* __restrict__ D2, const double* __restrict__ bb,
-                                                 const double* __restrict__ Z, const double* __restrict__ ur,
+                                                 const double* __restrict__ Z, const double* __restrict__ ur, const int* __restrict__ m_in,
                                                  double* __restrict__ T2, double* __restrict__ R2, double* __restrict__ r2) {
   const int c = n - kImuDim;
+  const bool full = *m_in <= n;  // m <= n: plain uncompressed update, all rows explicit (k_rows), no Gram part
   const size_t total = (size_t)n * n;
   for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
     const int a = (int)(e / n), b = (int)(e % n);
     double tv = 0.0, rv = 0.0;
-    if (a >= kImuDim && b >= kImuDim) {
+    if (!full && a >= kImuDim && b >= kImuDim) {
       const int ac = a - kImuDim, bc = b - kImuDim;
       // the Gram kernel wrote upper tiles only
       const bool upper = (ac / GT) <= (bc / GT);
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256) k_assemble(int n, int ld, int K, int nspl
   // beta
   for (int a = blockIdx.x * 256 + threadIdx.x; a < n; a += gridDim.x * 256) {
     double v = 0.0;
-    if (a >= kImuDim) {
+    if (!full && a >= kImuDim) {
       const int ac = a - kImuDim;
       double s = 0.0;
       for (int k = 0; k < K; ++k) s += Z[(size_t)k * c + ac] * ur[k];
@@ -156,79 +157,109 @@ __global__ void __launch_bounds__(256) k_assemble(int n, int ld, int K, int nspl
   }
 }
 
-// Head rows: stacked rows 0..14 pass through the reference's QR untouched (msckf.h:1343-1363 with 15 zero
-// leading columns).  They belong to the first accepted feature(s) in stacking order.  Single CTA.
+// Explicit stacked rows ("head rows"), one CTA per feature.
+//  * m > n : the reference's QR leaves stacked rows 0..14 untouched (15 zero leading columns of H_o,
+//            msckf.h:1343-1363); they enter the compressed system as themselves.  hcap = 15.
+//  * m <= n: the reference's Q is square, i.e. the update is the plain uncompressed EKF update in the full
+//            measurement space (orthogonal invariance) -- every stacked row is explicit, hcap = m, and the
+//            Gram part is switched off (k_assemble).
+// Row t of feature j is A_j(:,t)^T [X_j | r_j] with A_j(:,t) = Q e_{3+t},  Q = H0 H1 H2 = I - V T V^T (compact WY,
+// exact reflectors tau_k = 2 / v_k^T v_k in fp64): every entry of Q costs O(1) from V (2L x 3) and T (3 x 3).
 template <class S>
-__global__ void __launch_bounds__(256) k_head(int N, int n, int ld, const int* __restrict__ obs_off, const int* __restrict__ clone_idx,
-                                             const int* __restrict__ accept, const int* __restrict__ row_off,
+__global__ void __launch_bounds__(128) k_rows(int N, int n, int ld, const int* __restrict__ obs_off, const int* __restrict__ clone_idx,
+                                             const int* __restrict__ accept, const int* __restrict__ row_off, const int* __restrict__ m_in,
                                              const S* __restrict__ Xg, const S* __restrict__ rg, const S* __restrict__ Vg,
                                              const S* __restrict__ taug, const double* __restrict__ Z, double du, double dv,
-                                             double* __restrict__ T2, double* __restrict__ R2, double* __restrict__ r2, int Lmax) {
-  extern __shared__ double sh[];  // cols[18][2*Lmax]
+                                             double* __restrict__ T2, double* __restrict__ R2, double* __restrict__ r2) {
+  extern __shared__ double sh[];  // V[2L][3] | W[2L][3]
+  const int j = blockIdx.x;
+  if (!accept[j]) return;
+  const int m = *m_in;
+  const bool full = m <= n;
+  const int hcap = full ? m : kImuDim;
+  const int h0 = row_off[j];
+  if (h0 >= hcap) return;
   const int c = n - kImuDim;
+  const int o0 = obs_off[j], L = obs_off[j + 1] - o0, L2 = 2 * L;
+  const int nh = min(L2 - 3, hcap - h0);
   const int tid = threadIdx.x;
-  __shared__ double s_dot[18];
-  __shared__ double s_adu[15][3];
-  for (int j = 0; j < N; ++j) {
-    if (!accept[j]) continue;
-    const int h0 = row_off[j];
-    if (h0 >= kImuDim) break;  // offsets are non-decreasing
-    const int o0 = obs_off[j], L = obs_off[j + 1] - o0, L2 = 2 * L;
-    const int rho = L2 - 3;
-    const int nh = min(rho, kImuDim - h0);
-    const int ncol = 3 + nh;
-    const int ldc = 2 * Lmax;
-    // cols(:,q) = Q e_q = H0 H1 H2 e_q, q = 0..2+nh  (q<3: U_j, q>=3: the head columns of A_j)
-    for (int e = tid; e < ncol * L2; e += 256) { const int q = e / L2, row = e % L2; sh[q * ldc + row] = (row == q) ? 1.0 : 0.0; }
-    __syncthreads();
-    for (int k = 2; k >= 0; --k) {
-      const double tk = (double)taug[3 * j + k];
-      if (tid < ncol) {
-        double s = 0.0;
-        for (int row = k; row < L2; ++row) s += (double)Vg[3 * (2 * (size_t)o0 + row) + k] * sh[tid * ldc + row];
-        s_dot[tid] = tk * s;
-      }
-      __syncthreads();
-      for (int e = tid; e < ncol * L2; e += 256) {
-        const int q = e / L2, row = e % L2;
-        if (row >= k) sh[q * ldc + row] -= s_dot[q] * (double)Vg[3 * (2 * (size_t)o0 + row) + k];
-      }
-      __syncthreads();
+  double* V = sh;
+  double* W = sh + 3 * L2;
+  __shared__ double s_g[6], s_T[9], s_Wd[9], s_s[3], s_adu[kImuDim][3];
+  for (int e = tid; e < 3 * L2; e += 128) V[e] = (double)Vg[3 * 2 * (size_t)o0 + e];
+  __syncthreads();
+  if (tid < 6) {  // v_k^T v_l : (0,0) (1,1) (2,2) (0,1) (0,2) (1,2)
+    const int ka[6] = {0, 1, 2, 0, 0, 1}, kb[6] = {0, 1, 2, 1, 2, 2};
+    double s = 0.0;
+    for (int a = 0; a < L2; ++a) s += V[3 * a + ka[tid]] * V[3 * a + kb[tid]];
+    s_g[tid] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tau[3];
+    for (int k = 0; k < 3; ++k) tau[k] = ((double)taug[3 * j + k] != 0.0) ? 2.0 / s_g[k] : 0.0;
+    double T[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    T[0][0] = tau[0]; T[1][1] = tau[1]; T[2][2] = tau[2];
+    T[0][1] = -tau[1] * T[0][0] * s_g[3];
+    T[0][2] = -tau[2] * (T[0][0] * s_g[4] + T[0][1] * s_g[5]);
+    T[1][2] = -tau[2] * T[1][1] * s_g[5];
+    for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) s_T[3 * k + l] = T[k][l];
+  }
+  __syncthreads();
+  for (int a = tid; a < L2; a += 128)
+    for (int l = 0; l < 3; ++l) W[3 * a + l] = V[3 * a] * s_T[l] + V[3 * a + 1] * s_T[3 + l] + V[3 * a + 2] * s_T[6 + l];
+  __syncthreads();
+  if (tid < 9) {  // Wd = sum_a d_a w_a^T w_a
+    const int k = tid / 3, l = tid % 3;
+    double s = 0.0;
+    for (int a = 0; a < L2; ++a) s += ((a & 1) ? dv : du) * W[3 * a + k] * W[3 * a + l];
+    s_Wd[tid] = s;
+  } else if (tid < 12) {  // s = sum_a r_a w_a
+    const int l = tid - 9;
+    double s = 0.0;
+    for (int a = 0; a < L2; ++a) s += (double)rg[2 * (size_t)o0 + a] * W[3 * a + l];
+    s_s[l] = s;
+  }
+  __syncthreads();
+  // Q^T D Q entry for columns b, b2 of Q
+  auto qdq = [&](int b, int b2) {
+    const double db = (b & 1) ? dv : du, db2 = (b2 & 1) ? dv : du;
+    const double wb_vb2 = W[3 * b] * V[3 * b2] + W[3 * b + 1] * V[3 * b2 + 1] + W[3 * b + 2] * V[3 * b2 + 2];
+    const double wb2_vb = W[3 * b2] * V[3 * b] + W[3 * b2 + 1] * V[3 * b + 1] + W[3 * b2 + 2] * V[3 * b + 2];
+    double quad = 0.0;
+    for (int k = 0; k < 3; ++k)
+      for (int l = 0; l < 3; ++l) quad += V[3 * b + k] * s_Wd[3 * k + l] * V[3 * b2 + l];
+    return ((b == b2) ? db : 0.0) - db * wb_vb2 - db2 * wb2_vb + quad;
+  };
+  auto qent = [&](int a, int b) {  // Q[a][b]
+    return ((a == b) ? 1.0 : 0.0) - (W[3 * a] * V[3 * b] + W[3 * a + 1] * V[3 * b + 1] + W[3 * a + 2] * V[3 * b + 2]);
+  };
+  // r rows and the R_o block of this feature restricted to the explicit rows
+  for (int e = tid; e < nh * (nh + 1); e += 128) {
+    const int t = e / (nh + 1), u = e % (nh + 1);
+    const int b = 3 + t;
+    if (u == nh) {
+      r2[h0 + t] = (double)rg[2 * (size_t)o0 + b] - (s_s[0] * V[3 * b] + s_s[1] * V[3 * b + 1] + s_s[2] * V[3 * b + 2]);
+    } else {
+      R2[(size_t)(h0 + t) * ld + (h0 + u)] = qdq(b, 3 + u);
     }
-    // A_h^T D U (nh x 3)
-    if (tid < nh * 3) {
-      const int t = tid / 3, q = tid % 3;
-      double s = 0.0;
-      for (int row = 0; row < L2; ++row) s += sh[(3 + t) * ldc + row] * ((row & 1) ? dv : du) * sh[q * ldc + row];
-      s_adu[t][q] = s;
-    }
-    __syncthreads();
-    // r_h, R_hh
-    for (int e = tid; e < nh * (nh + 1); e += 256) {
-      const int t = e / (nh + 1), u = e % (nh + 1);
-      double s = 0.0;
-      if (u == nh) {
-        for (int row = 0; row < L2; ++row) s += sh[(3 + t) * ldc + row] * (double)rg[2 * (size_t)o0 + row];
-        r2[h0 + t] = s;
-      } else {
-        for (int row = 0; row < L2; ++row) s += sh[(3 + t) * ldc + row] * ((row & 1) ? dv : du) * sh[(3 + u) * ldc + row];
-        R2[(size_t)(h0 + t) * ld + (h0 + u)] = s;
-      }
-    }
-    // H_h rows and R_hH rows: nonzero only in the track's clone blocks
-    for (int e = tid; e < nh * L * 6; e += 256) {
-      const int t = e / (L * 6), rem = e % (L * 6), i = rem / 6, b = rem % 6;
-      const int col = 6 * clone_idx[o0 + i] + b;
-      const double x0 = (double)Xg[12 * (size_t)(o0 + i) + b], x1 = (double)Xg[12 * (size_t)(o0 + i) + 6 + b];
-      const double a0 = sh[(3 + t) * ldc + 2 * i], a1 = sh[(3 + t) * ldc + 2 * i + 1];
-      const double hv = a0 * x0 + a1 * x1;
-      double rv = du * a0 * x0 + dv * a1 * x1;
+  }
+  if (!full && tid < nh * 3) s_adu[tid / 3][tid % 3] = qdq(3 + tid / 3, tid % 3);  // A_h^T D U
+  __syncthreads();
+  // H rows (and, when compressing, the coupling rows R_hH = A_h^T D Pi_j X_j)
+  for (int e = tid; e < nh * L * 6; e += 128) {
+    const int t = e / (L * 6), rem = e % (L * 6), i = rem / 6, bb = rem % 6;
+    const int b = 3 + t;
+    const int col = 6 * clone_idx[o0 + i] + bb;
+    const double x0 = (double)Xg[12 * (size_t)(o0 + i) + bb], x1 = (double)Xg[12 * (size_t)(o0 + i) + 6 + bb];
+    const double q0 = qent(2 * i, b), q1 = qent(2 * i + 1, b);
+    T2[(size_t)(h0 + t) * ld + kImuDim + col] = q0 * x0 + q1 * x1;
+    if (!full) {
+      double rv = du * q0 * x0 + dv * q1 * x1;
       for (int q = 0; q < 3; ++q) rv -= s_adu[t][q] * Z[(size_t)(3 * j + q) * c + col];
-      T2[(size_t)(h0 + t) * ld + kImuDim + col] = hv;
       R2[(size_t)(h0 + t) * ld + kImuDim + col] = rv;
       R2[(size_t)(kImuDim + col) * ld + (h0 + t)] = rv;
     }
-    __syncthreads();
   }
 }
 

@@ -80,14 +80,21 @@ __global__ void __launch_bounds__(256) k_gemm_s(int n, int ld, const double* __r
 // Rank-revealing Cholesky in natural order ("skip" variant): index k is dropped when its pivot falls below
 // thr * (original diagonal) -- i.e. row k of Q'' is (numerically) in the span of the previous ones.  Dropped
 // rows/columns are removed from the factor (L_kk = 1, rest 0).  Single CTA, blocked (32), lower triangle in place.
+// decide = 1: rank decisions are taken here (pivot <= thr * original diagonal, or rank cap reached) and written to keep[].
+// decide = 0: keep[] is given (decided on the Gram matrix of the basis, k_gamma); only non-positive pivots are dropped.
 __global__ void __launch_bounds__(1024) k_chol(int n, int ld, double* __restrict__ A, int* __restrict__ keep, double thr,
-                                              int* __restrict__ rank_out) {
+                                              int* __restrict__ rank_out, const int* __restrict__ m_in, int decide) {
   extern __shared__ double sm[];
   double* d0 = sm;                       // [n]
   double* D = d0 + ((n + 1) & ~1);       // [32][33]
   double* Lp = D + 32 * 33;              // [(n) x 33] panel rows below the diagonal block
+  int* skeep = reinterpret_cast<int*>(Lp + (size_t)n * 33);  // [n]
+  __shared__ int s_rank;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int k = tid; k < n; k += 1024) d0[k] = A[(size_t)k * ld + k];
+  // the stacked system has m rows: span(Q'') cannot have more than min(m, n) dimensions
+  const int rank_cap = min(*m_in, n);
+  for (int k = tid; k < n; k += 1024) { d0[k] = A[(size_t)k * ld + k]; skeep[k] = decide ? 1 : keep[k]; }
+  if (tid == 0) s_rank = 0;
   __syncthreads();
   for (int kb = 0; kb < n; kb += 32) {
     const int nb = min(32, n - kb);
@@ -97,18 +104,21 @@ __global__ void __launch_bounds__(1024) k_chol(int n, int ld, double* __restrict
     }
     __syncthreads();
     if (warp == 0) {
+      int rank_now = s_rank;
       for (int j = 0; j < nb; ++j) {
         const double piv = D[j * 33 + j];
         const double dj0 = d0[kb + j];
-        const bool drop = !(dj0 > 0.0) || !(piv > thr * dj0);
+        const bool drop = decide ? (!(dj0 > 0.0) || !(piv > thr * dj0) || rank_now >= rank_cap)
+                                 : (skeep[kb + j] == 0 || !(piv > 0.0));
+        if (!drop) rank_now++;
         __syncwarp();
         if (drop) {
-          if (lane == 0) { keep[kb + j] = 0; D[j * 33 + j] = 1.0; }
+          if (lane == 0) { skeep[kb + j] = 0; D[j * 33 + j] = 1.0; }
           if (lane > j && lane < nb) D[lane * 33 + j] = 0.0;
           if (lane < j) D[j * 33 + lane] = 0.0;
         } else {
           const double ljj = sqrt(piv);
-          if (lane == 0) { keep[kb + j] = 1; D[j * 33 + j] = ljj; }
+          if (lane == 0) { skeep[kb + j] = 1; D[j * 33 + j] = ljj; }
           if (lane > j && lane < nb) D[lane * 33 + j] /= ljj;
           __syncwarp();
           if (lane > j && lane < nb) {
@@ -118,6 +128,7 @@ __global__ void __launch_bounds__(1024) k_chol(int n, int ld, double* __restrict
         }
         __syncwarp();
       }
+      if (lane == 0) s_rank = rank_now;
     }
     __syncthreads();
     for (int e = tid; e < nb * nb; e += 1024) {
@@ -132,7 +143,7 @@ __global__ void __launch_bounds__(1024) k_chol(int n, int ld, double* __restrict
       for (int j = 0; j < nb; ++j) {
         double v = A[(size_t)row * ld + kb + j];
         for (int cc = 0; cc < j; ++cc) v -= x[cc] * D[j * 33 + cc];
-        const bool kp = keep[kb + j] != 0;  // written by warp 0 before the barrier above
+        const bool kp = skeep[kb + j] != 0;  // written by warp 0 before the barrier above
         x[j] = kp ? v / D[j * 33 + j] : 0.0;
         A[(size_t)row * ld + kb + j] = x[j];
         Lp[(size_t)(row - r0) * 33 + j] = x[j];
@@ -155,14 +166,32 @@ __global__ void __launch_bounds__(1024) k_chol(int n, int ld, double* __restrict
     __syncthreads();
   }
   // dropped rows: clear the part of the row left of the diagonal that earlier panels produced
-  for (int k = 0; k < n; ++k) {
-    if (keep[k]) continue;
-    for (int cc = tid; cc < k; cc += 1024) A[(size_t)k * ld + cc] = 0.0;
+  for (int e = tid; e < n * n; e += 1024) {
+    const int k = e / n, cc = e % n;
+    if (cc < k && !skeep[k]) A[(size_t)k * ld + cc] = 0.0;
   }
-  if (tid == 0) {
-    int r = 0;
-    for (int k = 0; k < n; ++k) r += keep[k];
-    *rank_out = r;
+  for (int k = tid; k < n; k += 1024) keep[k] = skeep[k];
+  if (tid == 0) *rank_out = s_rank;
+}
+
+// Gram matrix of the basis Q'' = [E_h | H_c]:  Gamma = [[I_h, H_h], [H_h^T, Lambda]]  (all of it is already in T'').
+// Its rank-revealing Cholesky decides which basis vectors are independent -- a purely geometric decision,
+// unaffected by how large the prior covariance is relative to the measurement noise.
+__global__ void __launch_bounds__(256) k_gamma(int n, int ld, const double* __restrict__ T2, const int* __restrict__ m_in,
+                                              double* __restrict__ Gm) {
+  const int m = *m_in;
+  const bool full = m <= n;
+  const int h = full ? m : kImuDim;
+  const size_t total = (size_t)n * n;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int a = (int)(e / n), b = (int)(e % n);
+    double v;
+    if (full) v = (a == b && a < h) ? 1.0 : 0.0;  // all rows explicit and orthonormal: Gamma = I_m
+    else if (a < kImuDim && b < kImuDim) v = (a == b && a < h) ? 1.0 : 0.0;
+    else if (a < kImuDim) v = T2[(size_t)a * ld + b];
+    else if (b < kImuDim) v = T2[(size_t)b * ld + a];
+    else v = T2[(size_t)a * ld + b];
+    Gm[(size_t)a * ld + b] = v;
   }
 }
 
@@ -173,12 +202,16 @@ __global__ void __launch_bounds__(256) k_trsm(int n, int ld, const double* __res
   extern __shared__ double sm[];
   double* Ws = sm;              // [n][33]
   double* D = Ws + (size_t)n * 33;  // [32][33]
+  double* Lpan = D + 32 * 33;       // [n][33] panel of L below the diagonal block
+  int* skeep = reinterpret_cast<int*>(Lpan + (size_t)n * 33);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int col0 = blockIdx.x * 32;
+  for (int k = tid; k < n; k += 256) skeep[k] = keep[k];
+  __syncthreads();
   for (int e = tid; e < n * 32; e += 256) {
     const int row = e / 32, cc = e % 32, col = col0 + cc;
     double v = 0.0;
-    if (keep[row]) {
+    if (skeep[row]) {
       if (col < n) v = TP[(size_t)row * ld + col];
       else if (col == n) v = r2[row];
     }
@@ -187,9 +220,14 @@ __global__ void __launch_bounds__(256) k_trsm(int n, int ld, const double* __res
   __syncthreads();
   for (int kb = 0; kb < n; kb += 32) {
     const int nb = min(32, n - kb);
+    const int r0 = kb + nb;
     for (int e = tid; e < nb * nb; e += 256) {
       const int i = e / nb, j = e % nb;
       D[i * 33 + j] = (j <= i) ? Lm[(size_t)(kb + i) * ld + kb + j] : 0.0;
+    }
+    for (int e = tid; e < (n - r0) * nb; e += 256) {  // coalesced panel load
+      const int i = e / nb, j = e % nb;
+      Lpan[(size_t)i * 33 + j] = Lm[(size_t)(r0 + i) * ld + kb + j];
     }
     __syncthreads();
     if (warp == 0) {
@@ -197,18 +235,16 @@ __global__ void __launch_bounds__(256) k_trsm(int n, int ld, const double* __res
         const int row = kb + j;
         double x = Ws[(size_t)row * 33 + lane];
         for (int cc = 0; cc < j; ++cc) x -= D[j * 33 + cc] * Ws[(size_t)(kb + cc) * 33 + lane];
-        Ws[(size_t)row * 33 + lane] = keep[row] ? x / D[j * 33 + j] : 0.0;
+        Ws[(size_t)row * 33 + lane] = skeep[row] ? x / D[j * 33 + j] : 0.0;
       }
     }
     __syncthreads();
-    const int r0 = kb + nb;
     for (int e = tid; e < (n - r0) * 32; e += 256) {
-      const int row = r0 + e / 32, cc = e % 32;
+      const int i = e / 32, cc = e % 32;
       double s = 0.0;
-      const double* lrow = Lm + (size_t)row * ld + kb;
 #pragma unroll 8
-      for (int j = 0; j < nb; ++j) s += lrow[j] * Ws[(size_t)(kb + j) * 33 + cc];
-      Ws[(size_t)row * 33 + cc] -= s;
+      for (int j = 0; j < nb; ++j) s += Lpan[(size_t)i * 33 + j] * Ws[(size_t)(kb + j) * 33 + cc];
+      Ws[(size_t)(r0 + i) * 33 + cc] -= s;
     }
     __syncthreads();
   }

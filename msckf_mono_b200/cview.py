@@ -202,6 +202,28 @@ class CFilter:
         n = self._chk(self._f("last_delta_x")(self.h, out.ctypes.data_as(_dp), C.c_int(cap)), "last_delta_x")
         return out[:n].copy()
 
+    def packQueued(self):
+        """the batch queued by update()/finish() in the engine's flat SoA form (engine view only)."""
+        cap_t, cap_o = 8192, 8192 * 64
+        off = np.zeros(cap_t + 1, dtype=np.int32)
+        obs = np.zeros(2 * cap_o)
+        idx = np.zeros(cap_o, dtype=np.int32)
+        n = self._chk(self._f("pack_queued")(self.h, off.ctypes.data_as(_ip), obs.ctypes.data_as(_dp), idx.ctypes.data_as(_ip),
+                                            C.c_int(cap_t), C.c_int(cap_o)), "pack_queued")
+        tot = int(off[n])
+        return off[:n + 1].copy(), obs[:2 * tot].copy(), idx[:tot].copy()
+
+    def engineHandle(self):
+        fn = self._f("engine")
+        fn.restype = C.c_void_p
+        return fn(self.h)
+
+    def marginalizeLaunch(self):
+        self._chk(self._f("marginalize_launch")(self.h), "marginalize_launch")
+
+    def marginalizeCollect(self):
+        self._chk(self._f("marginalize_collect")(self.h), "marginalize_collect")
+
     def queuedTracks(self):
         cap = 8192
         ids = np.zeros(cap, dtype=np.uint64)

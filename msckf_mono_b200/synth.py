@@ -245,6 +245,23 @@ def make_window_workload(n_features=300, n_clones=30, seq=0, imu_per_frame=10, d
             "frames": frames, "landmarks": pts_G, "traj": traj, "t0": t0}
 
 
+def corrupt_observations(wl, frac_gross=0.1, frac_mild=0.15, seed=0):
+    """Turn some landmarks of a window workload into outliers: `gross` ones get a large offset in a few
+    frames (triangulation cost / cheirality / gate reject them), `mild` ones a small offset (borderline)."""
+    rng = np.random.default_rng(seed)
+    frames = wl["frames"]
+    n = len(frames[0]["add"][1])
+    kinds = rng.random(n)
+    for k, fr in enumerate(frames):
+        obs = fr["add"][0] if fr["add"] is not None else fr["update"][0]
+        for j in range(n):
+            if kinds[j] < frac_gross and k % 3 == 1:
+                obs[j] += rng.normal(0, 0.3, 2)
+            elif kinds[j] < frac_gross + frac_mild and k % 2 == 0:
+                obs[j] += rng.normal(0, 0.012, 2)
+    return wl
+
+
 def make_stream_workload(n_frames=200, seq=0, max_features=100, imu_per_frame=10, dT=0.005,
                          pixel_sigma=1.0, imu_noise_frac=0.05, n_landmarks=6000,
                          max_track_length=50, max_cam_states=30, isotropic=False, dropout=0.02):
@@ -316,7 +333,7 @@ def make_stream_workload(n_frames=200, seq=0, max_features=100, imu_per_frame=10
             "frames": frames, "landmarks": pts_G, "traj": traj, "t0": t0}
 
 
-def drive(filt, wl, upto=None, marginalize_last=True, prune=True, on_frame=None):
+def drive(filt, wl, upto=None, marginalize_last=True, prune=True, on_frame=None, prune_redundant=False):
     """Run a workload through any object exposing the MSCKF<_S> surface
     (call order of datasets/asl_msckf.cpp:233-294).  `upto` = number of frames."""
     filt.initialize(wl["camera"], wl["noise"], wl["params"], wl["imu_state"])
@@ -332,6 +349,8 @@ def drive(filt, wl, upto=None, marginalize_last=True, prune=True, on_frame=None)
         last = k == len(frames) - 1
         if (not last) or marginalize_last:
             filt.marginalize()
+            if prune_redundant:
+                filt.pruneRedundantStates()
             if prune:
                 filt.pruneEmptyStates()
         if on_frame is not None:

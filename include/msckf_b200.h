@@ -92,6 +92,8 @@ int msckf_b200_launch(msckf_b200_engine* e);
 int msckf_b200_launch_timed(msckf_b200_engine* e, float* ms);
 /* with option key 1 set, per-kernel device times of the last launch (launch order); returns the count */
 int msckf_b200_kernel_times(msckf_b200_engine* e, float* ms, const char** names, int cap);
+/* with option key 1 set, %globaltimer stamps (ns) taken by the tail kernel at its phase boundaries; 0-terminated */
+int msckf_b200_tail_profile(msckf_b200_engine* e, unsigned long long* out, int cap);
 /* update_async + fetch */
 int msckf_b200_update(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks, msckf_b200_report* report);
 /* covariance / pose gather of pruneEmptyStates msckf.h:685-761 and pruneRedundantStates :616-681:

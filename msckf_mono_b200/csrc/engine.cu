@@ -14,6 +14,7 @@
 #include "gram_kernels.cuh"
 #include "state_kernels.cuh"
 #include "tail_kernels.cuh"
+#include "tail_cluster.cuh"
 
 namespace {
 thread_local std::string g_err;
@@ -26,6 +27,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 constexpr int kMaxSplit = 16;
+constexpr int kTailCluster = 8;  // portable cluster size: the serial EKF tail runs on 8 SMs of one GPC
 constexpr size_t kSmemBudget = 220 * 1024;
 
 static const double kChi2_005[99] = {
@@ -50,6 +52,7 @@ struct EngineBase {
   virtual int launch() = 0;
   virtual int launch_timed(float* ms) = 0;
   virtual int kernel_times(float* ms, const char** names, int cap) = 0;
+  virtual int tail_profile(unsigned long long* out, int cap) = 0;
   bool profile = false;
   int dtype = 0, device = 0, Mmax = 0, Tmax = 0, Omax = 0;
   int M = 0;
@@ -65,11 +68,13 @@ struct Engine : EngineBase {
   S *d_P = nullptr, *d_P2 = nullptr, *d_poses = nullptr, *d_poses2 = nullptr;
   int *d_off = nullptr, *d_idx = nullptr, *d_cm = nullptr, *d_tri = nullptr, *d_valid = nullptr, *d_src = nullptr,
       *d_accept = nullptr, *d_rows = nullptr, *d_rowoff = nullptr, *d_scratch = nullptr, *d_keep = nullptr, *d_m = nullptr,
-      *d_rank = nullptr, *d_keepclones = nullptr;
+      *d_rank = nullptr, *d_keepclones = nullptr, *d_cmeff = nullptr;
+  unsigned long long* d_csnap = nullptr;
+  unsigned long long* d_prof = nullptr;
   S *d_obs = nullptr, *d_pfg = nullptr, *d_pfg_given = nullptr, *d_gamma = nullptr, *d_Xg = nullptr, *d_rg = nullptr,
     *d_Vg = nullptr, *d_taug = nullptr;
   double *d_Z = nullptr, *d_Yq = nullptr, *d_ur = nullptr, *d_G1p = nullptr, *d_G2p = nullptr, *d_D1 = nullptr, *d_D2 = nullptr,
-         *d_bb = nullptr, *d_T2 = nullptr, *d_R2 = nullptr, *d_r2 = nullptr, *d_TP = nullptr, *d_S2 = nullptr, *d_W = nullptr,
+         *d_bb = nullptr, *d_T2 = nullptr, *d_R2 = nullptr, *d_r2 = nullptr, *d_TP = nullptr, *d_S2 = nullptr, *d_W = nullptr, *d_G = nullptr,
          *d_y = nullptr, *d_dx = nullptr;
   // pinned host
   int *h_off = nullptr, *h_idx = nullptr, *h_flags = nullptr /*cm,tri,valid,accept: 4*Tmax*/, *h_mr = nullptr /*m, rank*/;
@@ -117,6 +122,10 @@ struct Engine : EngineBase {
     CK(cudaMalloc(&d_idx, sizeof(int) * O));
     for (int** p : {&d_cm, &d_tri, &d_valid, &d_src, &d_accept, &d_rows, &d_scratch}) CK(cudaMalloc(p, sizeof(int) * T));
     CK(cudaMalloc(&d_rowoff, sizeof(int) * (T + 1)));
+    CK(cudaMalloc(&d_cmeff, sizeof(int) * T));
+    CK(cudaMalloc(&d_csnap, sizeof(unsigned long long)));
+    CK(cudaMalloc(&d_prof, sizeof(unsigned long long) * 80));
+    CK(cudaMemsetAsync(d_prof, 0, sizeof(unsigned long long) * 80, stream));
     CK(cudaMalloc(&d_keep, sizeof(int) * nmax));
     CK(cudaMalloc(&d_m, sizeof(int) * 2));
     d_rank = d_m + 1;
@@ -137,7 +146,7 @@ struct Engine : EngineBase {
     CK(cudaMalloc(&d_D1, sizeof(double) * 36 * Mmax));
     CK(cudaMalloc(&d_D2, sizeof(double) * 36 * Mmax));
     CK(cudaMalloc(&d_bb, sizeof(double) * 6 * Mmax));
-    for (double** p : {&d_T2, &d_R2, &d_TP, &d_S2, &d_W}) CK(cudaMalloc(p, sizeof(double) * (size_t)ld * nmax));
+    for (double** p : {&d_T2, &d_R2, &d_TP, &d_S2, &d_W, &d_G}) CK(cudaMalloc(p, sizeof(double) * (size_t)ld * nmax));
     CK(cudaMalloc(&d_r2, sizeof(double) * nmax));
     CK(cudaMalloc(&d_y, sizeof(double) * nmax));
     CK(cudaMalloc(&d_dx, sizeof(double) * nmax));
@@ -153,12 +162,9 @@ struct Engine : EngineBase {
     CK(cudaMallocHost(&h_st, sizeof(mb::DevState<S>)));
     // opt in to large dynamic shared memory
     CK(cudaFuncSetAttribute(mb::k_tri<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_jac<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_jac<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_jac<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_jac<S, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_jac<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_tail<S, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_tail<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaStreamSynchronize(stream));
     return 0;
   }
@@ -166,8 +172,8 @@ struct Engine : EngineBase {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     void* dv[] = {d_st, d_P, d_P2, d_poses, d_poses2, d_off, d_idx, d_cm, d_tri, d_valid, d_src, d_accept, d_rows, d_rowoff,
-                  d_scratch, d_keep, d_m, d_keepclones, d_obs, d_pfg, d_pfg_given, d_gamma, d_Xg, d_rg, d_Vg, d_taug, d_Z, d_Yq,
-                  d_ur, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_T2, d_R2, d_TP, d_S2, d_W, d_r2, d_y, d_dx};
+                  d_scratch, d_keep, d_m, d_keepclones, d_cmeff, d_csnap, d_prof, d_obs, d_pfg, d_pfg_given, d_gamma, d_Xg, d_rg, d_Vg, d_taug, d_Z, d_Yq,
+                  d_ur, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_T2, d_R2, d_TP, d_S2, d_W, d_G, d_r2, d_y, d_dx};
     for (void* p : dv) if (p) cudaFree(p);
     void* hv[] = {h_off, h_idx, h_flags, h_mr, h_obs, h_pfg_in, h_pfg, h_gamma, h_st};
     for (void* p : hv) if (p) cudaFreeHost(p);
@@ -224,12 +230,6 @@ struct Engine : EngineBase {
     CK(cudaGetLastError());
     M += 1;
     return 0;
-  }
-
-  template <int WPB>
-  void launch_jac(const mb::FeatArgs<S>& a, size_t smem) {
-    const int grid = (a.n_tracks + WPB - 1) / WPB;
-    mb::k_jac<S, WPB><<<grid, WPB * 32, smem, stream>>>(a);
   }
 
   int update_async(int mode, const msckf_b200_tracks* tr) override {
@@ -291,35 +291,22 @@ struct Engine : EngineBase {
     mb::FeatArgs<S> a;
     a.n_tracks = N; a.M = M; a.Lmax = Lmax; a.ldp = ldp;
     a.obs_off = d_off; a.obs = d_obs; a.clone_idx = d_idx; a.poses = d_poses; a.P = d_P; a.st = d_st;
-    a.pfg = d_pfg; a.cm_ok = d_cm; a.tri_ok = d_tri; a.valid = d_valid; a.src = d_src;
+    a.pfg = d_pfg; a.counter_snap = d_csnap; a.cm_eff = d_cmeff; a.cm_ok = d_cm; a.tri_ok = d_tri; a.valid = d_valid; a.src = d_src;
     a.pfg_given = (mode == MSCKF_B200_RESIDUALIZE) ? d_pfg_given : nullptr;
     a.accept = d_accept; a.gamma = d_gamma; a.rows = d_rows; a.Xg = d_Xg; a.rg = d_rg; a.Vg = d_Vg; a.taug = d_taug;
     a.Z = d_Z; a.Yq = d_Yq; a.ur = d_ur;
     const size_t pose_bytes = 16 + sizeof(S) * mb::kPoseStride * (size_t)M;
     if (mode != MSCKF_B200_RESIDUALIZE) {
-      const size_t smem = pose_bytes + sizeof(S) * 4 * 12 * (size_t)Lmax;
+      const size_t smem = pose_bytes + sizeof(S) * 4 * 14 * (size_t)Lmax;
       if (smem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_tri shared memory");
       mb::k_tri<S, 4><<<(N + 3) / 4, 128, smem, stream>>>(a);
       launches++;
       mark("k_tri");
     }
     if (mode != MSCKF_B200_TRIANGULATE) {
-      mb::k_resolve<S><<<1, 1024, 0, stream>>>(a, d_st, mode == MSCKF_B200_RESIDUALIZE ? 1 : 0, d_scratch);
-      launches++;
-      mark("k_resolve");
-      const size_t per_warp = sizeof(S) * mb::jac_warp_smem_elems<S>(Lmax);
-      if (pose_bytes + per_warp > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_jac shared memory");
-      int wpb = (int)std::min<size_t>(8, (kSmemBudget - pose_bytes) / per_warp);
-      wpb = wpb >= 8 ? 8 : wpb >= 4 ? 4 : wpb >= 2 ? 2 : 1;
-      // keep enough CTAs in flight to cover the SMs when the batch is small
-      while (wpb > 1 && (N + wpb - 1) / wpb < 148) wpb >>= 1;
-      const size_t smem = pose_bytes + per_warp * wpb;
-      switch (wpb) {
-        case 8: launch_jac<8>(a, smem); break;
-        case 4: launch_jac<4>(a, smem); break;
-        case 2: launch_jac<2>(a, smem); break;
-        default: launch_jac<1>(a, smem); break;
-      }
+      const size_t jsmem = mb::jac_smem_bytes<S>(Lmax, M);
+      if (jsmem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_jac shared memory");
+      mb::k_jac<S><<<N, mb::JT, jsmem, stream>>>(a, d_st, mode == MSCKF_B200_RESIDUALIZE ? 1 : 0);
       launches++;
       mark("k_jac");
       mb::k_scan<<<1, 1024, 0, stream>>>(N, d_rows, d_rowoff, d_m);
@@ -352,33 +339,36 @@ struct Engine : EngineBase {
       mb::k_gemm_s<<<tg, 256, 0, stream>>>(n, ld, d_TP, d_T2, d_R2, d_S2);
       mark("k_gemm_s");
       launches += 2;
-      const size_t chol_smem = sizeof(double) * (((n + 1) & ~1) + 32 * 33 + (size_t)n * 33) + sizeof(int) * n;
-      if (chol_smem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_chol shared memory");
-      // rank decision on the basis Gram matrix (d_W is free until k_trsm), then the factorisation of S''
-      mb::k_gamma<<<agrid, 256, 0, stream>>>(n, ld, d_T2, d_m, d_W);
-      mb::k_chol<<<1, 1024, chol_smem, stream>>>(n, ld, d_W, d_keep, rank_thr, d_rank, d_m, 1);
-      launches += 2;
-      mark("k_rank");
-      mb::k_chol<<<1, 1024, chol_smem, stream>>>(n, ld, d_S2, d_keep, rank_thr, d_rank, d_m, 0);
+      // rank decision + Cholesky + substitution + covariance/state update: one cluster kernel (scratch for Gamma: d_G)
+      {
+        const int ldt = (n + 3) & ~3;
+        auto smem_for = [&](int NB) { return sizeof(double) * ((size_t)2 * NB * (NB + 1) + 2 + (size_t)2 * NB * ldt + ((n + 1) & ~1)) + sizeof(int) * NB + 64; };
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kTailCluster, 1, 1);
+        cfg.blockDim = dim3(mb::kTailThreads, 1, 1);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kTailCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (smem_for(32) <= kSmemBudget) {
+          cfg.dynamicSmemBytes = smem_for(32);
+          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 32>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_keep, rank_thr, d_rank, (const int*)d_m,
+                                (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_P, ldp, d_st, d_poses, d_dx, profile ? d_prof : (unsigned long long*)nullptr));
+        } else if (smem_for(16) <= kSmemBudget) {
+          cfg.dynamicSmemBytes = smem_for(16);
+          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 16>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_keep, rank_thr, d_rank, (const int*)d_m,
+                                (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_P, ldp, d_st, d_poses, d_dx, profile ? d_prof : (unsigned long long*)nullptr));
+        } else return fail(MSCKF_B200_ERR_CAPACITY, "k_tail shared memory");
+      }
       launches++;
-      mark("k_chol");
-      const size_t trsm_smem = sizeof(double) * (2 * (size_t)n * 33 + 32 * 33) + sizeof(int) * n;
-      if (trsm_smem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_trsm shared memory");
-      mb::k_trsm<<<(n + 1 + 31) / 32, 256, trsm_smem, stream>>>(n, ld, d_S2, d_keep, d_TP, d_r2, d_W, d_y);
-      launches++;
-      mark("k_trsm");
-      mb::k_syrk_apply<S><<<tg, 256, 0, stream>>>(n, ld, d_W, d_P, ldp);
-      launches++;
-      mark("k_syrk_apply");
-      mb::k_inject<S><<<1, 256, sizeof(double) * n, stream>>>(n, ld, M, d_W, d_y, d_st, d_poses, d_dx, d_m, d_rank);
-      launches++;
-      mark("k_inject");
+      mark("k_tail");
     }
     CK(cudaGetLastError());
     if (timed_region) CK(cudaEventRecord(ev_t1, stream));
     // report back (pinned), still asynchronous
     if (mode != MSCKF_B200_RESIDUALIZE) {
-      CK(cudaMemcpyAsync(h_flags, d_cm, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(h_flags, mode == MSCKF_B200_MARGINALIZE ? d_cmeff : d_cm, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
       CK(cudaMemcpyAsync(h_flags + Tmax, d_tri, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
       CK(cudaMemcpyAsync(h_pfg, d_pfg, sizeof(S) * 3 * (size_t)N, cudaMemcpyDeviceToHost, stream));
     }
@@ -526,6 +516,13 @@ struct Engine : EngineBase {
     return 0;
   }
 
+  int tail_profile(unsigned long long* out, int cap) override {
+    CK(cudaSetDevice(device));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaMemcpy(out, d_prof, sizeof(unsigned long long) * std::min(cap, 80), cudaMemcpyDeviceToHost));
+    return std::min(cap, 80);
+  }
+
   int kernel_times(float* ms, const char** names, int cap) override {
     CK(cudaSetDevice(device));
     CK(cudaStreamSynchronize(stream));
@@ -589,6 +586,7 @@ int msckf_b200_stage(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tr
 int msckf_b200_launch(msckf_b200_engine* e) { return e->impl->launch(); }
 int msckf_b200_launch_timed(msckf_b200_engine* e, float* ms) { return e->impl->launch_timed(ms); }
 int msckf_b200_kernel_times(msckf_b200_engine* e, float* ms, const char** names, int cap) { return e->impl->kernel_times(ms, names, cap); }
+int msckf_b200_tail_profile(msckf_b200_engine* e, unsigned long long* out, int cap) { return e->impl->tail_profile(out, cap); }
 int msckf_b200_set_option(msckf_b200_engine* e, int key, double value) {
   if (key == 0) { e->impl->rank_thr = value; return 0; }
   if (key == 1) { e->impl->profile = value != 0; return 0; }

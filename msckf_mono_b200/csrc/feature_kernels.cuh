@@ -1,8 +1,8 @@
 // msckf_mono_b200/csrc/feature_kernels.cuh
 // Per-feature stage of the MSCKF measurement update, one warp per feature track:
 //   k_tri     : checkMotion (msckf.h:980-1025) + inverse-depth LM triangulation (msckf.h:1147-1285)
-//   k_resolve : loop-A bookkeeping of marginalize() (msckf.h:352-399, incl. the p_f_G_vec index quirk of :419)
-//   k_jac     : calcResidual (:960-978), calcMeasJacobian (:905-958, left null space by 3 Householder
+//   k_jac     : one CTA per track: loop-A bookkeeping of marginalize() (msckf.h:352-399, incl. the p_f_G_vec index
+//               quirk of :419), calcResidual (:960-978), calcMeasJacobian (:905-958, left null space by 3 Householder
 //               reflectors of the column-pivoted QR of H_f), gatingTest (:1103-1124)
 //   k_scan    : ordered stacking offsets (msckf.h:433-445)
 // Clone poses are staged into shared memory with one TMA bulk copy per CTA.
@@ -22,9 +22,11 @@ struct FeatArgs {
   const DevState<S>* st;
   // k_tri out
   S* pfg;       // [N*3]
+  unsigned long long* counter_snap;  // num_feature_tracks_residualized_ before this batch (read by k_jac)
+  int* cm_eff;  // [N] "not rejected by checkMotion" (msckf.h:354) as reported to the host
   int* cm_ok;   // [N] checkMotion result
   int* tri_ok;  // [N] initializePosition validity
-  // k_resolve out
+  // loop-A bookkeeping out (k_jac prologue)
   int* valid;  // [N]
   int* src;    // [N] index of the track whose p_f_G loop B uses (msckf.h:419)
   // k_jac out
@@ -41,50 +43,61 @@ struct FeatArgs {
   double* ur;          // [3N]      U_j^T r_j
 };
 
-// Eigen::LDLT (diagonal pivoting) solve of a symmetric 3x3 system, msckf.h:1222.
+// Eigen::LDLT (diagonal pivoting) solve of a symmetric 3x3 system, msckf.h:1222, register-only.
+// Eigen's unblocked LDLT is left-looking: at step k it picks the largest |diagonal| among the not yet eliminated
+// (and not yet updated) entries, i.e. the elimination order is the descending order of the ORIGINAL |a_ii|
+// (first index wins ties).  The symmetric permutation is applied with uniform branches, then the recurrences of
+// ldlt_inplace<Lower>::unblocked follow literally.
 template <class S>
-__device__ __forceinline__ void ldlt3_solve(S A[3][3], const S b[3], S x[3]) {
-  int tr[3];
-  S temp[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    int idx = k;
-    S big = tabs(A[k][k]);
-    for (int i = k + 1; i < 3; ++i)
-      if (tabs(A[i][i]) > big) { big = tabs(A[i][i]); idx = i; }
-    tr[k] = idx;
-    if (idx != k) {
-      for (int j = 0; j < k; ++j) { S t = A[k][j]; A[k][j] = A[idx][j]; A[idx][j] = t; }
-      for (int i = idx + 1; i < 3; ++i) { S t = A[i][k]; A[i][k] = A[i][idx]; A[i][idx] = t; }
-      { S t = A[k][k]; A[k][k] = A[idx][idx]; A[idx][idx] = t; }
-      for (int i = k + 1; i < idx; ++i) { S t = A[i][k]; A[i][k] = A[idx][i]; A[idx][i] = t; }
-    }
-    if (k > 0) {
-      for (int j = 0; j < k; ++j) temp[j] = A[j][j] * A[k][j];
-      S s = 0;
-      for (int j = 0; j < k; ++j) s += A[k][j] * temp[j];
-      A[k][k] -= s;
-      for (int i = k + 1; i < 3; ++i) {
-        S t = 0;
-        for (int j = 0; j < k; ++j) t += A[i][j] * temp[j];
-        A[i][k] -= t;
-      }
-    }
-    const S akk = A[k][k];
-    if (tabs(akk) > S(0))
-      for (int i = k + 1; i < 3; ++i) A[i][k] /= akk;
+__device__ __forceinline__ void ldlt3_solve(S a00, S a01, S a02, S a11, S a12, S a22, const S b[3], S x[3]) {
+  const S d0a = tabs(a00), d1a = tabs(a11), d2a = tabs(a22);
+  int p0 = 0;
+  if (d1a > d0a) p0 = 1;
+  if (d2a > (p0 == 0 ? d0a : d1a)) p0 = 2;
+  int p1, p2;
+  {
+    const int q0 = (p0 == 0) ? 1 : 0, q1 = (p0 == 2) ? 1 : 2;  // remaining two, ascending
+    const S dq0 = (q0 == 0) ? d0a : d1a, dq1 = (q1 == 1) ? d1a : d2a;
+    // Eigen swaps k <-> biggest: the other remaining index may have moved into p0's slot; the search order of the
+    // tail after the swap is (slot1, slot2).  After swapping 0 <-> p0 the slots hold: p0==1 -> (0, 2); p0==2 -> (1, 0); p0==0 -> (1, 2)
+    const int s1 = (p0 == 0) ? 1 : (p0 == 1 ? 0 : 1), s2 = (p0 == 0) ? 2 : (p0 == 1 ? 2 : 0);
+    const S ds1 = (s1 == 0) ? d0a : (s1 == 1 ? d1a : d2a), ds2 = (s2 == 0) ? d0a : (s2 == 1 ? d1a : d2a);
+    (void)q0; (void)q1; (void)dq0; (void)dq1;
+    if (ds2 > ds1) { p1 = s2; p2 = s1; } else { p1 = s1; p2 = s2; }
   }
-  x[0] = b[0]; x[1] = b[1]; x[2] = b[2];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { S t = x[k]; x[k] = x[tr[k]]; x[tr[k]] = t; }
-  x[1] -= A[1][0] * x[0];
-  x[2] -= A[2][0] * x[0] + A[2][1] * x[1];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) x[i] = (tabs(A[i][i]) > S(0)) ? x[i] / A[i][i] : S(0);
-  x[1] -= A[2][1] * x[2];
-  x[0] -= A[1][0] * x[1] + A[2][0] * x[2];
-#pragma unroll
-  for (int k = 2; k >= 0; --k) { S t = x[k]; x[k] = x[tr[k]]; x[tr[k]] = t; }
+  // permuted entries m_ij = a[p_i][p_j]
+  auto pick = [&](int i, int j) -> S {
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    if (lo == 0) return hi == 0 ? a00 : (hi == 1 ? a01 : a02);
+    if (lo == 1) return hi == 1 ? a11 : a12;
+    return a22;
+  };
+  const S m00 = pick(p0, p0), m10 = pick(p1, p0), m20 = pick(p2, p0), m11 = pick(p1, p1), m21 = pick(p2, p1), m22 = pick(p2, p2);
+  const S c0 = b[p0 == 0 ? 0 : (p0 == 1 ? 1 : 2)], c1 = b[p1 == 0 ? 0 : (p1 == 1 ? 1 : 2)], c2 = b[p2 == 0 ? 0 : (p2 == 1 ? 1 : 2)];
+  // k = 0
+  const S dd0 = m00;
+  const bool v0 = tabs(dd0) > S(0);
+  const S l10 = v0 ? m10 / dd0 : m10, l20 = v0 ? m20 / dd0 : m20;
+  // k = 1
+  const S t0 = dd0 * l10;
+  const S dd1 = m11 - l10 * t0;
+  S l21 = m21 - l20 * t0;
+  const bool v1 = tabs(dd1) > S(0);
+  if (v1) l21 = l21 / dd1;
+  // k = 2
+  const S u0 = dd0 * l20, u1 = dd1 * l21;
+  const S dd2 = m22 - (l20 * u0 + l21 * u1);
+  // solve
+  S y0 = c0, y1 = c1 - l10 * y0, y2 = c2 - (l20 * y0 + l21 * y1);
+  y0 = (tabs(dd0) > S(0)) ? y0 / dd0 : S(0);
+  y1 = (tabs(dd1) > S(0)) ? y1 / dd1 : S(0);
+  y2 = (tabs(dd2) > S(0)) ? y2 / dd2 : S(0);
+  y1 = y1 - l21 * y2;
+  y0 = y0 - (l10 * y1 + l20 * y2);
+  // un-permute
+  x[0] = (p0 == 0) ? y0 : (p1 == 0 ? y1 : y2);
+  x[1] = (p0 == 1) ? y0 : (p1 == 1 ? y1 : y2);
+  x[2] = (p0 == 2) ? y0 : (p1 == 2 ? y1 : y2);
 }
 
 // sum over the track's observations of the reprojection cost (msckf.h:1027-1047), warp-reduced
@@ -114,8 +127,12 @@ __global__ void __launch_bounds__(WPB * 32) k_tri(FeatArgs<S> a) {
   if (t >= a.n_tracks) return;
   const int o0 = a.obs_off[t], L = a.obs_off[t + 1] - o0;
   const int* idx = a.clone_idx + o0;
-  const S* z = a.obs + 2 * (size_t)o0;
-  S* rel = rel_all + (size_t)warp * a.Lmax * 12;
+  const S* zg = a.obs + 2 * (size_t)o0;
+  S* rel = rel_all + (size_t)warp * a.Lmax * 14;
+  S* z = rel + (size_t)a.Lmax * 12;  // observations staged in shared memory (read ~100x by the LM loops)
+  for (int e = lane; e < 2 * L; e += 32) z[e] = zg[e];
+  __syncwarp();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.counter_snap = a.st->num_residualized;
   // first clone: camera -> world
   const S* pose0 = poses + kPoseStride * idx[0];
   S C0[9];
@@ -210,10 +227,9 @@ __global__ void __launch_bounds__(WPB * 32) k_tri(FeatArgs<S> a) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) s[k] = warp_sum(s[k]);
     do {
-      S A[3][3] = {{s[0] + lambda, s[1], s[2]}, {s[1], s[3] + lambda, s[4]}, {s[2], s[4], s[5] + lambda}};
       const S b[3] = {s[6], s[7], s[8]};
       S delta[3];
-      ldlt3_solve(A, b, delta);
+      ldlt3_solve(s[0] + lambda, s[1], s[2], s[3] + lambda, s[4], s[5] + lambda, b, delta);
       const S ns[3] = {sol[0] - delta[0], sol[1] - delta[1], sol[2] - delta[2]};
       delta_norm = tsqrt<S>(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
       const S new_cost = track_cost(rel, z, L, lane, ns);
@@ -251,137 +267,133 @@ __global__ void __launch_bounds__(WPB * 32) k_tri(FeatArgs<S> a) {
   }
 }
 
-// Loop A of marginalize() (msckf.h:352-399) as a bookkeeping pass over the per-track flags.
-// Single CTA.  mode 0: marginalize semantics; mode 1: every track valid at its own/given position.
-template <class S>
-__global__ void k_resolve(FeatArgs<S> a, DevState<S>* st, int mode, int* pushed_scratch) {
-  __shared__ int s_head_end, s_total_pushed;
-  __shared__ unsigned long long s_counter;
-  __shared__ int s_scan[1024];
-  const int N = a.n_tracks;
-  const int tid = threadIdx.x;
-  if (mode == 1) {
-    for (int k = tid; k < N; k += blockDim.x) { a.valid[k] = 1; a.src[k] = k; }
-    return;
-  }
-  // head: walk sequentially while the residualised-track counter is <= 3 (checkMotion not yet applied)
-  if (tid == 0) {
-    unsigned long long counter = st->num_residualized;
-    int k = 0;
-    for (; k < N && counter <= 3; ++k) {
-      pushed_scratch[k] = 1;  // checkMotion not consulted -> initializePosition ran -> p_f_G pushed
-      a.cm_ok[k] = 1;         // report: "not rejected by checkMotion" (msckf.h:354)
-      const int v = a.tri_ok[k];
-      a.valid[k] = v;
-      if (v) counter++;
-    }
-    s_head_end = k;
-    s_counter = counter;
-  }
-  __syncthreads();
-  const int he = s_head_end;
-  for (int k = he + tid; k < N; k += blockDim.x) {
-    const int cm = a.cm_ok[k];
-    pushed_scratch[k] = cm;
-    a.valid[k] = cm && a.tri_ok[k];
-  }
-  __syncthreads();
-  // exclusive scan of pushed[] (chunked, blockDim.x == 1024) -> position in p_f_G_vec; inverse map pi[]
-  int carry = 0;
-  for (int base = 0; base < N; base += 1024) {
-    const int k = base + tid;
-    const int v = (k < N) ? pushed_scratch[k] : 0;
-    s_scan[tid] = v;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      int t = (tid >= o) ? s_scan[tid - o] : 0;
-      __syncthreads();
-      s_scan[tid] += t;
-      __syncthreads();
-    }
-    const int incl = s_scan[tid];
-    if (k < N && v) a.src[carry + incl - 1] = k;  // pi[rank] = k  (temporarily stored in src[])
-    const int tot = s_scan[1023];
-    __syncthreads();
-    carry += tot;
-  }
-  if (tid == 0) s_total_pushed = carry;
-  __syncthreads();
-  const int total = s_total_pushed;
-  // src[] currently holds pi[0..total); loop B reads p_f_G_vec[iter] = pfg[pi[iter]] when iter < total,
-  // else (out of bounds in the reference, UB) the track's own position.  Resolve in place via scratch.
-  __syncthreads();
-  for (int k = tid; k < N; k += blockDim.x) pushed_scratch[k] = (k < total) ? a.src[k] : k;
-  __syncthreads();
-  unsigned long long shifted = 0, oob = 0, nvalid = 0;
-  for (int k = tid; k < N; k += blockDim.x) {
-    const int sidx = pushed_scratch[k];
-    a.src[k] = sidx;
-    if (a.valid[k]) {
-      if (k >= he) nvalid++;
-      if (k < total) { if (sidx != k) shifted++; } else oob++;
-    }
-  }
-  // block-reduce the three counters
-  __shared__ unsigned long long s_red[3];
-  if (tid == 0) { s_red[0] = s_red[1] = s_red[2] = 0; }
-  __syncthreads();
-  if (shifted) atomicAdd(&s_red[0], shifted);
-  if (oob) atomicAdd(&s_red[1], oob);
-  if (nvalid) atomicAdd(&s_red[2], nvalid);
-  __syncthreads();
-  if (tid == 0) {
-    st->pfg_shifted += s_red[0];
-    st->pfg_oob += s_red[1];
-    st->num_residualized = s_counter + s_red[2];
-  }
-}
-
 // packed lower-triangular symmetric storage
 __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
 
-template <class S>
-__host__ __device__ inline size_t jac_warp_smem_elems(int L) {
-  // X 12L | r 2L | V 6L | U64 6L doubles (= 12L floats worst case) | w 2L | p 2L | Ypacked L(2L+1)
-  return (size_t)36 * L + (size_t)L * (2 * L + 1) + 4;
+constexpr int JT = 128;  // threads per feature in k_jac
+
+template <class T>
+__device__ __forceinline__ T block_sum(T v, T* red /*[JT/32]*/) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T t = red[0];
+#pragma unroll
+  for (int w = 1; w < JT / 32; ++w) t += red[w];
+  return t;
 }
 
-template <class S, int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_jac(FeatArgs<S> a) {
+template <class S>
+__host__ __device__ inline size_t jac_smem_bytes(int L, int M) {
+  // bar 16 | poses M*8 S | U64 6L doubles | X 12L | r 2L | V 6L | wv 2L | pv 2L | Ypacked L(2L+1)  (S) | pad
+  return 16 + sizeof(S) * kPoseStride * (size_t)M + 16 + sizeof(double) * 6 * (size_t)L +
+         sizeof(S) * ((size_t)24 * L + (size_t)L * (2 * L + 1)) + 16;
+}
+
+// calcResidual + calcMeasJacobian + gatingTest for one feature per CTA (JT threads), with loop A's bookkeeping
+// (msckf.h:352-399: valid flags, num_feature_tracks_residualized_, and the p_f_G_vec index of :419) folded into
+// the prologue.  mode 0: marginalize semantics; mode 1: every track valid at its given position.
+template <class S>
+__global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   S* poses = reinterpret_cast<S*>(smem_raw + 16);
-  S* ws_all = poses + (size_t)a.M * kPoseStride;
   stage_table_tma(poses, a.poses, (unsigned)(a.M * kPoseStride * sizeof(S)), bar);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x * WPB + warp;
-  if (t >= a.n_tracks) return;
+  __shared__ double redd[JT / 32];
+  __shared__ S reds[JT / 32];
+  __shared__ int redi[JT / 32];
+  __shared__ int s_he, s_valid, s_src, s_pushed_t;
+  __shared__ unsigned long long s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int t = blockIdx.x;
+  const int N = a.n_tracks;
   const int c = 6 * a.M;
+  // ------------------------------------------------------------------ loop-A bookkeeping
+  if (mode == 1) {
+    if (tid == 0) { s_valid = 1; s_src = t; }
+  } else {
+    if (tid == 0) {
+      unsigned long long counter = *a.counter_snap;
+      int k = 0;
+      for (; k < N && counter <= 3; ++k)  // checkMotion is not consulted while the counter is <= 3 (msckf.h:354)
+        if (a.tri_ok[k]) counter++;
+      s_he = k;
+      s_cnt = counter;
+    }
+    __syncthreads();
+    const int he = s_he;
+    // pushed(k): the track pushed a position into p_f_G_vec (msckf.h:374)
+    int before = 0, total = 0, nvalid_tail = 0;
+    for (int k = tid; k < N; k += JT) {
+      const int cm = a.cm_ok[k];
+      const int pushed = (k < he) ? 1 : cm;
+      total += pushed;
+      if (k < t) before += pushed;
+      if (k >= he && cm && a.tri_ok[k]) nvalid_tail++;
+    }
+    auto isum = [&](int v) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      __syncthreads();
+      if (lane == 0) redi[tid >> 5] = v;
+      __syncthreads();
+      return redi[0] + redi[1] + redi[2] + redi[3];
+    };
+    total = isum(total);
+    before = isum(before);
+    nvalid_tail = isum(nvalid_tail);
+    if (tid == 0) {
+      const int cm_t = a.cm_ok[t];
+      const int pushed_t = (t < he) ? 1 : cm_t;
+      const int valid_t = (t < he) ? a.tri_ok[t] : (cm_t && a.tri_ok[t]);
+      // loop B reads p_f_G_vec[iter] (msckf.h:419): the iter-th pushed track when it exists, else (UB in the
+      // reference) the track's own position
+      int src = t;
+      if (t < total && !(before == t && pushed_t)) {  // fast path: nothing before t was rejected -> p_f_G_vec[t] is t's own
+        int seen = 0;
+        for (int k = 0; k < N; ++k) {
+          const int pushed = (k < he) ? 1 : a.cm_ok[k];
+          if (pushed) { if (seen == t) { src = k; break; } seen++; }
+        }
+      }
+      s_valid = valid_t; s_src = src; s_pushed_t = pushed_t;
+      a.cm_eff[t] = pushed_t;
+      if (valid_t) {
+        if (t < total) { if (src != t) atomicAdd(&st_rw->pfg_shifted, 1ull); } else atomicAdd(&st_rw->pfg_oob, 1ull);
+      }
+      if (t == 0) st_rw->num_residualized = s_cnt + (unsigned long long)nvalid_tail;
+    }
+  }
+  __syncthreads();
+  const int valid = s_valid, src = s_src;
   const int o0 = a.obs_off[t], L = a.obs_off[t + 1] - o0, L2 = 2 * L;
   double* Zr = a.Z + (size_t)3 * t * c;
   double* Yr = a.Yq + (size_t)3 * t * c;
-  if (!a.valid[t]) {  // not residualised: contributes nothing
-    for (int k = lane; k < 3 * c; k += 32) { Zr[k] = 0.0; Yr[k] = 0.0; }
-    if (lane == 0) { a.accept[t] = 0; a.gamma[t] = S(0); a.rows[t] = 0; a.ur[3 * t] = a.ur[3 * t + 1] = a.ur[3 * t + 2] = 0.0; }
+  if (tid == 0) { a.valid[t] = valid; a.src[t] = src; }
+  if (!valid) {  // not residualised: contributes nothing
+    for (int k = tid; k < 3 * c; k += JT) { Zr[k] = 0.0; Yr[k] = 0.0; }
+    if (tid == 0) { a.accept[t] = 0; a.gamma[t] = S(0); a.rows[t] = 0; a.ur[3 * t] = a.ur[3 * t + 1] = a.ur[3 * t + 2] = 0.0; }
     return;
   }
-  const int* idx = a.clone_idx + o0;
-  const S* z = a.obs + 2 * (size_t)o0;
-  S* wbase = ws_all + (size_t)warp * jac_warp_smem_elems<S>(a.Lmax);
-  // U in fp64 (8-byte aligned: the per-warp region starts 16-byte aligned and its size is even in S units)
-  double* U = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(wbase) + 7) & ~uintptr_t(7));
+  // ------------------------------------------------------------------ shared-memory carve-up
+  unsigned char* wp = smem_raw + 16 + sizeof(S) * kPoseStride * (size_t)a.M;
+  wp = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(wp) + 15) & ~uintptr_t(15));
+  double* U = reinterpret_cast<double*>(wp);  // [2L][3] fp64
   S* X = reinterpret_cast<S*>(U + 3 * L2);
   S* r = X + 12 * L;
   S* V = r + L2;
   S* wv = V + 3 * L2;
   S* pv = wv + L2;
   S* Y = pv + L2;
+  const int* idx = a.clone_idx + o0;
+  const S* z = a.obs + 2 * (size_t)o0;
   const DevState<S>* st = a.st;
   const S g[3] = {st->g[0], st->g[1], st->g[2]};
-  const S* pfsrc = a.pfg_given ? (a.pfg_given + 3 * t) : (a.pfg + 3 * a.src[t]);
+  const S* pfsrc = a.pfg_given ? (a.pfg_given + 3 * t) : (a.pfg + 3 * src);
   const S pf[3] = {pfsrc[0], pfsrc[1], pfsrc[2]};
   // ---- residual + measurement Jacobian blocks with the observability projection (msckf.h:915-950, 960-978)
-  for (int i = lane; i < L; i += 32) {
+  for (int i = tid; i < L; i += JT) {
     const S* ps = poses + kPoseStride * idx[i];
     S C[9];
     quat_to_rot(ps, C);
@@ -394,7 +406,6 @@ __global__ void __launch_bounds__(WPB * 32) k_jac(FeatArgs<S> a) {
     a.rg[2 * (size_t)(o0 + i)] = r0; a.rg[2 * (size_t)(o0 + i) + 1] = r1;
     const S iz = S(1) / Zc;
     const S J[2][3] = {{S(1) * iz, S(0) * iz, (-Xc / Zc) * iz}, {S(0) * iz, S(1) * iz, (-Yc / Zc) * iz}};
-    // skew(pc)
     const S sk[3][3] = {{S(0), -pc[2], pc[1]}, {pc[2], S(0), -pc[0]}, {-pc[1], pc[0], S(0)}};
     S A[2][6];
 #pragma unroll
@@ -429,7 +440,7 @@ __global__ void __launch_bounds__(WPB * 32) k_jac(FeatArgs<S> a) {
       }
     }
   }
-  __syncwarp();
+  __syncthreads();
   // ---- column-pivoted Householder QR of H_f (2L x 3): the trailing 2L-3 columns of Q are A_j (msckf.h:954-955)
   S tau[3];
 #pragma unroll
@@ -437,93 +448,101 @@ __global__ void __launch_bounds__(WPB * 32) k_jac(FeatArgs<S> a) {
     S nn[3] = {S(-1), S(-1), S(-1)};
     for (int cc = k; cc < 3; ++cc) {
       S sacc = 0;
-      for (int row = k + lane; row < L2; row += 32) sacc += V[3 * row + cc] * V[3 * row + cc];
-      nn[cc] = warp_sum(sacc);
+      for (int row = k + tid; row < L2; row += JT) sacc += V[3 * row + cc] * V[3 * row + cc];
+      nn[cc] = block_sum(sacc, reds);
     }
     int piv = k;
     S best = nn[k];
     for (int cc = k + 1; cc < 3; ++cc)
       if (nn[cc] > best) { best = nn[cc]; piv = cc; }
     if (piv != k)
-      for (int row = lane; row < L2; row += 32) { const S tmp = V[3 * row + k]; V[3 * row + k] = V[3 * row + piv]; V[3 * row + piv] = tmp; }
-    __syncwarp();
+      for (int row = tid; row < L2; row += JT) { const S tmp = V[3 * row + k]; V[3 * row + k] = V[3 * row + piv]; V[3 * row + piv] = tmp; }
+    __syncthreads();
     S tacc = 0;
-    for (int row = k + 1 + lane; row < L2; row += 32) tacc += V[3 * row + k] * V[3 * row + k];
-    const S tail = warp_sum(tacc);
+    for (int row = k + 1 + tid; row < L2; row += JT) tacc += V[3 * row + k] * V[3 * row + k];
+    const S tail = block_sum(tacc, reds);
     const S c0 = V[3 * k + k];
     S beta, tk;
+    __syncthreads();
     if (tail <= S(sizeof(S) == 4 ? 1.17549435e-38 : 2.2250738585072014e-308)) {
       beta = c0; tk = S(0);
-      for (int row = k + 1 + lane; row < L2; row += 32) V[3 * row + k] = S(0);
+      for (int row = k + 1 + tid; row < L2; row += JT) V[3 * row + k] = S(0);
     } else {
       beta = tsqrt<S>(c0 * c0 + tail);
       if (c0 >= S(0)) beta = -beta;
       const S dd = c0 - beta;
-      for (int row = k + 1 + lane; row < L2; row += 32) V[3 * row + k] /= dd;
+      for (int row = k + 1 + tid; row < L2; row += JT) V[3 * row + k] /= dd;
       tk = (beta - c0) / beta;
     }
     tau[k] = tk;
-    __syncwarp();
+    __syncthreads();
     if (tk != S(0)) {
       for (int cc = k + 1; cc < 3; ++cc) {
         S sacc = 0;
-        for (int row = k + 1 + lane; row < L2; row += 32) sacc += V[3 * row + k] * V[3 * row + cc];
-        S sdot = warp_sum(sacc) + V[3 * k + cc];
+        for (int row = k + 1 + tid; row < L2; row += JT) sacc += V[3 * row + k] * V[3 * row + cc];
+        S sdot = block_sum(sacc, reds) + V[3 * k + cc];
         sdot *= tk;
-        for (int row = k + 1 + lane; row < L2; row += 32) V[3 * row + cc] -= V[3 * row + k] * sdot;
-        __syncwarp();
-        if (lane == 0) V[3 * k + cc] -= sdot;
-        __syncwarp();
+        __syncthreads();
+        for (int row = k + 1 + tid; row < L2; row += JT) V[3 * row + cc] -= V[3 * row + k] * sdot;
+        if (tid == 0) V[3 * k + cc] -= sdot;
+        __syncthreads();
       }
     }
-    if (lane == 0) V[3 * k + k] = S(1);  // unit diagonal of the Householder vector
-    // zero above the diagonal of column k so V(:,k) is the full Householder vector v_k
-    if (lane == 0) for (int row = 0; row < k; ++row) V[3 * row + k] = S(0);
-    __syncwarp();
+    if (tid == 0) {
+      V[3 * k + k] = S(1);                                // unit diagonal of the Householder vector
+      for (int row = 0; row < k; ++row) V[3 * row + k] = S(0);  // zero above: V(:,k) is the full vector v_k
+    }
+    __syncthreads();
   }
-  // export v_k, tau for the head-row kernel
-  for (int e = lane; e < 3 * L2; e += 32) a.Vg[3 * 2 * (size_t)o0 + e] = V[e];
-  if (lane < 3) a.taug[3 * t + lane] = tau[lane];
-  // ---- exact reflectors for the Gram stage: H_k = I - tau64_k v_k v_k^T with tau64_k = 2 / (v_k^T v_k) evaluated in
-  // fp64 from the stored vectors.  Q = H_0 H_1 H_2 is then orthogonal to 1e-16 whatever the filter precision, so
-  // G_j = I - U_j U_j^T is an exact projector and the body Gram terms and the head rows (k_head) describe the same H_o.
+  // export v_k, tau for the explicit-row kernel
+  for (int e = tid; e < 3 * L2; e += JT) a.Vg[3 * 2 * (size_t)o0 + e] = V[e];
+  if (tid < 3) a.taug[3 * t + tid] = tau[tid];
+  // ---- exact reflectors for the Gram stage: H_k = I - tau64_k v_k v_k^T with tau64_k = 2 / (v_k^T v_k) in fp64, so that
+  // Q = H_0 H_1 H_2 is orthogonal to 1e-16 whatever the filter precision: G_j = I - U_j U_j^T is an exact projector
+  // and the body Gram terms and the explicit rows (k_rows) describe the same H_o.
   double tau64[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     double sacc = 0.0;
-    for (int row = k + lane; row < L2; row += 32) { const double vv = (double)V[3 * row + k]; sacc += vv * vv; }
-    const double vtv = warp_sum(sacc);
+    for (int row = k + tid; row < L2; row += JT) { const double vv = (double)V[3 * row + k]; sacc += vv * vv; }
+    const double vtv = block_sum(sacc, redd);
     tau64[k] = (tau[k] != S(0)) ? 2.0 / vtv : 0.0;
   }
   // ---- U = Q(:,0:3) = H0 H1 H2 [I3; 0]  (fp64)
-  for (int e = lane; e < 3 * L2; e += 32) U[e] = ((e / 3) == (e % 3)) ? 1.0 : 0.0;
-  __syncwarp();
+  for (int e = tid; e < 3 * L2; e += JT) U[e] = ((e / 3) == (e % 3)) ? 1.0 : 0.0;
+  __syncthreads();
 #pragma unroll
   for (int k = 2; k >= 0; --k) {
+    double sd[3];
     for (int cc = 0; cc < 3; ++cc) {
       double sacc = 0.0;
-      for (int row = k + lane; row < L2; row += 32) sacc += (double)V[3 * row + k] * U[3 * row + cc];
-      const double sdot = tau64[k] * warp_sum(sacc);
-      for (int row = k + lane; row < L2; row += 32) U[3 * row + cc] -= sdot * (double)V[3 * row + k];
+      for (int row = k + tid; row < L2; row += JT) sacc += (double)V[3 * row + k] * U[3 * row + cc];
+      sd[cc] = tau64[k] * block_sum(sacc, redd);
     }
-    __syncwarp();
+    __syncthreads();
+    for (int row = k + tid; row < L2; row += JT) {
+      const double vk = (double)V[3 * row + k];
+      U[3 * row] -= sd[0] * vk; U[3 * row + 1] -= sd[1] * vk; U[3 * row + 2] -= sd[2] * vk;
+    }
+    __syncthreads();
   }
   // U^T r in fp64 from the raw residual
   double urv[3];
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     double sacc = 0.0;
-    for (int row = lane; row < L2; row += 32) sacc += U[3 * row + q] * (double)r[row];
-    urv[q] = warp_sum(sacc);
+    for (int row = tid; row < L2; row += JT) sacc += U[3 * row + q] * (double)r[row];
+    urv[q] = block_sum(sacc, redd);
   }
   // ---- r~ = H2 H1 H0 r in the filter precision (r_o = r~[3:], used by the gate only)
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     S sacc = 0;
-    for (int row = k + lane; row < L2; row += 32) sacc += V[3 * row + k] * r[row];
-    const S sdot = tau[k] * warp_sum(sacc);
-    for (int row = k + lane; row < L2; row += 32) r[row] -= sdot * V[3 * row + k];
-    __syncwarp();
+    for (int row = k + tid; row < L2; row += JT) sacc += V[3 * row + k] * r[row];
+    const S sdot = tau[k] * block_sum(sacc, reds);
+    __syncthreads();
+    for (int row = k + tid; row < L2; row += JT) r[row] -= sdot * V[3 * row + k];
+    __syncthreads();
   }
   // ---- gating (msckf.h:1103-1124): gamma = r_o^T (H_o P H_o^T + u_var I)^-1 r_o with H_o = (Q^T X)[3:]
   // Y = X P_sub X^T, symmetric 2L x 2L, packed lower
@@ -531,7 +550,7 @@ __global__ void __launch_bounds__(WPB * 32) k_jac(FeatArgs<S> a) {
     const int npairs = L * (L + 1) / 2;
     const S* P = a.P;
     const int ldp = a.ldp;
-    for (int p = lane; p < npairs; p += 32) {
+    for (int p = tid; p < npairs; p += JT) {
       int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
       while (i * (i + 1) / 2 > p) --i;
       while ((i + 1) * (i + 2) / 2 <= p) ++i;
@@ -564,97 +583,102 @@ __global__ void __launch_bounds__(WPB * 32) k_jac(FeatArgs<S> a) {
       if (i != k) Y[pk(2 * i, 2 * k + 1)] = y01;
     }
   }
-  __syncwarp();
+  __syncthreads();
   // two-sided reflectors: Y <- H_k Y H_k on the trailing (>= k) block
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const S tk = tau[k];
     if (tk != S(0)) {
-      for (int ar = k + lane; ar < L2; ar += 32) {
+      for (int ar = k + tid; ar < L2; ar += JT) {
         S sacc = 0;
         for (int b = k; b <= ar; ++b) sacc += Y[pk(ar, b)] * V[3 * b + k];
         for (int b = ar + 1; b < L2; ++b) sacc += Y[pk(b, ar)] * V[3 * b + k];
         wv[ar] = sacc;
       }
-      __syncwarp();
+      __syncthreads();
       S aacc = 0;
-      for (int ar = k + lane; ar < L2; ar += 32) aacc += V[3 * ar + k] * wv[ar];
-      const S alpha = warp_sum(aacc);
+      for (int ar = k + tid; ar < L2; ar += JT) aacc += V[3 * ar + k] * wv[ar];
+      const S alpha = block_sum(aacc, reds);
       const S hc = tk * tk * alpha * S(0.5);
-      for (int ar = k + lane; ar < L2; ar += 32) pv[ar] = tk * wv[ar] - hc * V[3 * ar + k];
-      __syncwarp();
-      for (int ar = k + lane; ar < L2; ar += 32) {
-        const S va = V[3 * ar + k], pa = pv[ar];
-        for (int b = k; b <= ar; ++b) Y[pk(ar, b)] -= va * pv[b] + pa * V[3 * b + k];
+      for (int ar = k + tid; ar < L2; ar += JT) pv[ar] = tk * wv[ar] - hc * V[3 * ar + k];
+      __syncthreads();
+      const int nk = L2 - k, ntri = nk * (nk + 1) / 2;
+      for (int e = tid; e < ntri; e += JT) {
+        int ia = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while (ia * (ia + 1) / 2 > e) --ia;
+        while ((ia + 1) * (ia + 2) / 2 <= e) ++ia;
+        const int ib = e - ia * (ia + 1) / 2;
+        const int ar = k + ia, b = k + ib;
+        Y[pk(ar, b)] -= V[3 * ar + k] * pv[b] + pv[ar] * V[3 * b + k];
       }
-      __syncwarp();
+      __syncthreads();
     }
   }
   // S = Y[3:,3:] + u_var I ; Cholesky with the right-hand side r~[3:] carried as an extra row
   const S uvar = st->u_var;
-  for (int j = 3 + lane; j < L2; j += 32) Y[pk(j, j)] += uvar;
-  __syncwarp();
+  for (int j = 3 + tid; j < L2; j += JT) Y[pk(j, j)] += uvar;
   bool chol_ok = true;
   for (int j = 3; j < L2; ++j) {
+    __syncthreads();
     const S dj = Y[pk(j, j)];
     if (!(dj > S(0))) { chol_ok = false; break; }
     const S ljj = tsqrt<S>(dj);
-    __syncwarp();
-    for (int i = j + 1 + lane; i < L2; i += 32) Y[pk(i, j)] /= ljj;
-    if (lane == 0) { r[j] /= ljj; Y[pk(j, j)] = ljj; }
-    __syncwarp();
-    const S ej = r[j];
-    for (int i = j + 1 + lane; i < L2; i += 32) {
+    const S ej = r[j] / ljj;
+    for (int i = j + 1 + tid; i < L2; i += JT) Y[pk(i, j)] /= ljj;
+    __syncthreads();
+    if (tid == 0) r[j] = ej;
+    const int nk = L2 - j - 1, ntri = nk * (nk + 1) / 2;
+    for (int e = tid; e < ntri; e += JT) {
+      int ia = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while (ia * (ia + 1) / 2 > e) --ia;
+      while ((ia + 1) * (ia + 2) / 2 <= e) ++ia;
+      const int ib = e - ia * (ia + 1) / 2;
+      const int i = j + 1 + ia, cc = j + 1 + ib;
       const S lij = Y[pk(i, j)];
-      r[i] -= ej * lij;
-      for (int cc = j + 1; cc <= i; ++cc) Y[pk(i, cc)] -= lij * Y[pk(cc, j)];
+      Y[pk(i, cc)] -= lij * Y[pk(cc, j)];
+      if (ib == 0) r[i] -= ej * lij;  // one thread per row carries the right-hand side
     }
-    __syncwarp();
   }
+  __syncthreads();
   S gacc = 0;
-  for (int j = 3 + lane; j < L2; j += 32) gacc += r[j] * r[j];
-  S gam = warp_sum(gacc);
+  for (int j = 3 + tid; j < L2; j += JT) gacc += r[j] * r[j];
+  S gam = block_sum(gacc, reds);
   const int acc = chol_ok && (gam < st->chi2[L]);  // table[dof+1], dof = L-1 (msckf.h:433,:1117)
   if (!chol_ok) gam = S(1e30);
   // ---- compact outputs for the Gram stage
-  for (int k = lane; k < 3 * c; k += 32) { Zr[k] = 0.0; Yr[k] = 0.0; }
-  // M = U^T D U (3x3 symmetric), D = diag(u_var, v_var, u_var, ...)
-  double Mm[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = tid; k < 3 * c; k += JT) { Zr[k] = 0.0; Yr[k] = 0.0; }
+  double Mm[6] = {0, 0, 0, 0, 0, 0};  // M = U^T D U (3x3 symmetric), D = diag(u_var, v_var, u_var, ...)
   const double du = (double)st->u_var, dv = (double)st->v_var;
-  for (int row = lane; row < L2; row += 32) {
+  for (int row = tid; row < L2; row += JT) {
     const double dd = (row & 1) ? dv : du;
     const double u0 = U[3 * row], u1 = U[3 * row + 1], u2 = U[3 * row + 2];
     Mm[0] += dd * u0 * u0; Mm[1] += dd * u0 * u1; Mm[2] += dd * u0 * u2;
     Mm[3] += dd * u1 * u1; Mm[4] += dd * u1 * u2; Mm[5] += dd * u2 * u2;
   }
 #pragma unroll
-  for (int k = 0; k < 6; ++k) Mm[k] = warp_sum(Mm[k]);
+  for (int k = 0; k < 6; ++k) Mm[k] = block_sum(Mm[k], redd);
   const double M3[3][3] = {{Mm[0], Mm[1], Mm[2]}, {Mm[1], Mm[3], Mm[4]}, {Mm[2], Mm[4], Mm[5]}};
-  __syncwarp();
+  __syncthreads();
   if (acc) {
-    for (int i = lane; i < L; i += 32) {
-      const int col0 = 6 * idx[i];
-      double zb[3][6], yb[3][6];
+    for (int e = tid; e < L * 6; e += JT) {
+      const int i = e / 6, b = e % 6;
+      const int col = 6 * idx[i] + b;
+      const double xa = X[12 * i + b], xb = X[12 * i + 6 + b];
+      double zb[3], yb[3];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const double ua = U[3 * (2 * i) + q], ub = U[3 * (2 * i + 1) + q];
-#pragma unroll
-        for (int b = 0; b < 6; ++b) {
-          const double xa = X[12 * i + b], xb = X[12 * i + 6 + b];
-          zb[q][b] = ua * xa + ub * xb;
-          yb[q][b] = du * ua * xa + dv * ub * xb;
-        }
+        zb[q] = ua * xa + ub * xb;
+        yb[q] = du * ua * xa + dv * ub * xb;
       }
 #pragma unroll
-      for (int q = 0; q < 3; ++q)
-#pragma unroll
-        for (int b = 0; b < 6; ++b) {
-          Zr[(size_t)q * c + col0 + b] = zb[q][b];
-          Yr[(size_t)q * c + col0 + b] = yb[q][b] - 0.5 * (M3[q][0] * zb[0][b] + M3[q][1] * zb[1][b] + M3[q][2] * zb[2][b]);
-        }
+      for (int q = 0; q < 3; ++q) {
+        Zr[(size_t)q * c + col] = zb[q];
+        Yr[(size_t)q * c + col] = yb[q] - 0.5 * (M3[q][0] * zb[0] + M3[q][1] * zb[1] + M3[q][2] * zb[2]);
+      }
     }
   }
-  if (lane == 0) {
+  if (tid == 0) {
     a.accept[t] = acc;
     a.gamma[t] = gam;
     a.rows[t] = acc ? (L2 - 3) : 0;

@@ -144,16 +144,25 @@ __global__ void __launch_bounds__(256) k_assemble(int n, int ld, int K, int nspl
     T2[(size_t)a * ld + b] = tv;
     R2[(size_t)a * ld + b] = rv;
   }
-  // beta
-  for (int a = blockIdx.x * 256 + threadIdx.x; a < n; a += gridDim.x * 256) {
-    double v = 0.0;
-    if (!full && a >= kImuDim) {
+  // beta = blk(sum X^T r) - Z^T (U^T r): 32 columns x 8 k-groups per CTA, reduced through shared memory
+  __shared__ double part[8][33];
+  const int al = threadIdx.x & 31, kg = threadIdx.x >> 5;
+  for (int a0 = blockIdx.x * 32; a0 < n; a0 += gridDim.x * 32) {
+    const int a = a0 + al;
+    double s = 0.0;
+    if (!full && a < n && a >= kImuDim) {
       const int ac = a - kImuDim;
-      double s = 0.0;
-      for (int k = 0; k < K; ++k) s += Z[(size_t)k * c + ac] * ur[k];
-      v = bb[ac] - s;
+      for (int k = kg; k < K; k += 8) s += Z[(size_t)k * c + ac] * ur[k];
     }
-    r2[a] = v;
+    part[kg][al] = s;
+    __syncthreads();
+    if (kg == 0 && a < n) {
+      double t = 0.0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) t += part[g][al];
+      r2[a] = (!full && a >= kImuDim) ? bb[a - kImuDim] - t : 0.0;
+    }
+    __syncthreads();
   }
 }
 

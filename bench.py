@@ -294,8 +294,14 @@ def main():
         import ctypes as C
         buf = (C.c_ulonglong * 80)()
         capi.lib().msckf_b200_tail_profile(work.h, buf, 80)
-        st = [int(x) for x in buf if x]
+        st = [int(x) for x in list(buf)[:40] if x]
         print("tail stamps (us since start):", [round((x - st[0]) / 1e3, 1) for x in st], file=sys.stderr)
+        sj = []
+        for x in list(buf)[40:]:
+            if not x:
+                break
+            sj.append(int(x))
+        print("jac stamps (us since start):", [round((x - sj[0]) / 1e3, 1) for x in sj], file=sys.stderr)
     work.set_option(1, 0.0)
     kern_ms = {k: float(np.mean(v[1:])) for k, v in per.items()}
     dom = max(kern_ms, key=kern_ms.get)

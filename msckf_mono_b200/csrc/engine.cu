@@ -75,7 +75,7 @@ struct Engine : EngineBase {
     *d_Vg = nullptr, *d_taug = nullptr;
   double *d_Z = nullptr, *d_Yq = nullptr, *d_ur = nullptr, *d_G1p = nullptr, *d_G2p = nullptr, *d_D1 = nullptr, *d_D2 = nullptr,
          *d_bb = nullptr, *d_T2 = nullptr, *d_R2 = nullptr, *d_r2 = nullptr, *d_TP = nullptr, *d_S2 = nullptr, *d_W = nullptr, *d_G = nullptr,
-         *d_y = nullptr, *d_dx = nullptr;
+         *d_y = nullptr, *d_dx = nullptr, *d_idiag = nullptr;
   // pinned host
   int *h_off = nullptr, *h_idx = nullptr, *h_flags = nullptr /*cm,tri,valid,accept: 4*Tmax*/, *h_mr = nullptr /*m, rank*/;
   S *h_obs = nullptr, *h_pfg_in = nullptr, *h_pfg = nullptr, *h_gamma = nullptr;
@@ -148,6 +148,7 @@ struct Engine : EngineBase {
     CK(cudaMalloc(&d_bb, sizeof(double) * 6 * Mmax));
     for (double** p : {&d_T2, &d_R2, &d_TP, &d_S2, &d_W, &d_G}) CK(cudaMalloc(p, sizeof(double) * (size_t)ld * nmax));
     CK(cudaMalloc(&d_r2, sizeof(double) * nmax));
+    CK(cudaMalloc(&d_idiag, sizeof(double) * 2 * nmax));
     CK(cudaMalloc(&d_y, sizeof(double) * nmax));
     CK(cudaMalloc(&d_dx, sizeof(double) * nmax));
     CK(cudaMemsetAsync(d_dx, 0, sizeof(double) * nmax, stream));
@@ -173,7 +174,7 @@ struct Engine : EngineBase {
     if (stream) cudaStreamSynchronize(stream);
     void* dv[] = {d_st, d_P, d_P2, d_poses, d_poses2, d_off, d_idx, d_cm, d_tri, d_valid, d_src, d_accept, d_rows, d_rowoff,
                   d_scratch, d_keep, d_m, d_keepclones, d_cmeff, d_csnap, d_prof, d_obs, d_pfg, d_pfg_given, d_gamma, d_Xg, d_rg, d_Vg, d_taug, d_Z, d_Yq,
-                  d_ur, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_T2, d_R2, d_TP, d_S2, d_W, d_G, d_r2, d_y, d_dx};
+                  d_ur, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_T2, d_R2, d_TP, d_S2, d_W, d_G, d_r2, d_y, d_dx, d_idiag};
     for (void* p : dv) if (p) cudaFree(p);
     void* hv[] = {h_off, h_idx, h_flags, h_mr, h_obs, h_pfg_in, h_pfg, h_gamma, h_st};
     for (void* p : hv) if (p) cudaFreeHost(p);
@@ -295,6 +296,7 @@ struct Engine : EngineBase {
     a.pfg_given = (mode == MSCKF_B200_RESIDUALIZE) ? d_pfg_given : nullptr;
     a.accept = d_accept; a.gamma = d_gamma; a.rows = d_rows; a.Xg = d_Xg; a.rg = d_rg; a.Vg = d_Vg; a.taug = d_taug;
     a.Z = d_Z; a.Yq = d_Yq; a.ur = d_ur;
+    a.prof = profile ? (d_prof + 40) : nullptr;
     const size_t pose_bytes = 16 + sizeof(S) * mb::kPoseStride * (size_t)M;
     if (mode != MSCKF_B200_RESIDUALIZE) {
       const size_t smem = pose_bytes + sizeof(S) * 4 * 14 * (size_t)Lmax;
@@ -334,15 +336,15 @@ struct Engine : EngineBase {
       launches++;
       mark("k_rows");
       const dim3 tg((n + 31) / 32, (n + 31) / 32);
-      mb::k_gemm_tp<S><<<tg, 256, 0, stream>>>(n, ld, d_T2, d_P, ldp, d_TP);
+      mb::k_gemm_tp<S><<<tg, 64, 0, stream>>>(n, ld, d_T2, d_P, ldp, d_TP);
       mark("k_gemm_tp");
-      mb::k_gemm_s<<<tg, 256, 0, stream>>>(n, ld, d_TP, d_T2, d_R2, d_S2);
+      mb::k_gemm_s<<<tg, 64, 0, stream>>>(n, ld, d_TP, d_T2, d_R2, d_S2);
       mark("k_gemm_s");
       launches += 2;
       // rank decision + Cholesky + substitution + covariance/state update: one cluster kernel (scratch for Gamma: d_G)
       {
         const int ldt = (n + 3) & ~3;
-        auto smem_for = [&](int NB) { return sizeof(double) * ((size_t)2 * NB * (NB + 1) + 2 + (size_t)2 * NB * ldt + ((n + 1) & ~1)) + sizeof(int) * NB + 64; };
+        auto smem_for = [&](int NB) { return sizeof(double) * ((size_t)2 * NB * (NB + 1) + 2 + (size_t)2 * NB * ldt + ((n + 1) & ~1) + 2 * NB) + 64; };
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(kTailCluster, 1, 1);
         cfg.blockDim = dim3(mb::kTailThreads, 1, 1);
@@ -353,16 +355,25 @@ struct Engine : EngineBase {
         cfg.attrs = attr; cfg.numAttrs = 1;
         if (smem_for(32) <= kSmemBudget) {
           cfg.dynamicSmemBytes = smem_for(32);
-          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 32>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_keep, rank_thr, d_rank, (const int*)d_m,
+          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 32>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_R2 /*receives L (R'' is consumed by k_gemm_s)*/, d_keep, d_idiag, rank_thr, d_rank, (const int*)d_m,
                                 (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_P, ldp, d_st, d_poses, d_dx, profile ? d_prof : (unsigned long long*)nullptr));
         } else if (smem_for(16) <= kSmemBudget) {
           cfg.dynamicSmemBytes = smem_for(16);
-          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 16>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_keep, rank_thr, d_rank, (const int*)d_m,
+          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 16>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_R2 /*receives L (R'' is consumed by k_gemm_s)*/, d_keep, d_idiag, rank_thr, d_rank, (const int*)d_m,
                                 (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_P, ldp, d_st, d_poses, d_dx, profile ? d_prof : (unsigned long long*)nullptr));
         } else return fail(MSCKF_B200_ERR_CAPACITY, "k_tail shared memory");
       }
       launches++;
       mark("k_tail");
+      {
+        const int nt32 = (n + 31) / 32;
+        mb::k_syrk<S><<<nt32 * (nt32 + 1) / 2, 64, 0, stream>>>(n, ld, d_W, d_P, ldp, d_m);
+        launches++;
+        mark("k_syrk");
+        mb::k_inject<S><<<1, 1024, sizeof(double) * n, stream>>>(n, ld, M, d_W, d_y, d_st, d_poses, d_dx, d_m, d_rank);
+        launches++;
+        mark("k_inject");
+      }
     }
     CK(cudaGetLastError());
     if (timed_region) CK(cudaEventRecord(ev_t1, stream));

@@ -38,6 +38,7 @@ struct FeatArgs {
   S* rg;               // [sumL*2]  residuals
   S* Vg;               // [sumL*2*3] Householder vectors of the null-space projection (unit lower trapezoid)
   S* taug;             // [N*3]
+  unsigned long long* prof;  // optional: %globaltimer stamps of CTA 0's phases (profiling aid)
   double* Z;           // [3N x c]  U_j^T X_j scattered to clone columns
   double* Yq;          // [3N x c]  U_j^T D X_j - 1/2 (U_j^T D U_j) Z_j
   double* ur;          // [3N]      U_j^T r_j
@@ -284,6 +285,25 @@ __device__ __forceinline__ T block_sum(T v, T* red /*[JT/32]*/) {
   return t;
 }
 
+// three sums at once (one pair of barriers)
+__device__ __forceinline__ void block_sum3(double v[3], double* red /*[3 * JT/32]*/) {
+#pragma unroll
+  for (int q = 0; q < 3; ++q) v[q] = warp_sum(v[q]);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) red[3 * (threadIdx.x >> 5) + q] = v[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double t = red[q];
+#pragma unroll
+    for (int w = 1; w < JT / 32; ++w) t += red[3 * w + q];
+    v[q] = t;
+  }
+}
+
 template <class S>
 __host__ __device__ inline size_t jac_smem_bytes(int L, int M) {
   // bar 16 | poses M*8 S | U64 6L doubles | X 12L | r 2L | V 6L | wv 2L | pv 2L | Ypacked L(2L+1)  (S) | pad
@@ -301,6 +321,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   S* poses = reinterpret_cast<S*>(smem_raw + 16);
   stage_table_tma(poses, a.poses, (unsigned)(a.M * kPoseStride * sizeof(S)), bar);
   __shared__ double redd[JT / 32];
+  __shared__ double redd3[3 * (JT / 32)];
   __shared__ S reds[JT / 32];
   __shared__ int redi[JT / 32];
   __shared__ int s_he, s_valid, s_src, s_pushed_t;
@@ -309,6 +330,15 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   const int t = blockIdx.x;
   const int N = a.n_tracks;
   const int c = 6 * a.M;
+  int prof_i = 0;
+  auto stamp = [&]() {
+    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0 && prof_i < 30) {
+      unsigned long long tt;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt));
+      a.prof[prof_i++] = tt;
+    }
+  };
+  stamp();
   // ------------------------------------------------------------------ loop-A bookkeeping
   if (mode == 1) {
     if (tid == 0) { s_valid = 1; s_src = t; }
@@ -366,6 +396,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
     }
   }
   __syncthreads();
+  stamp();  // bookkeeping
   const int valid = s_valid, src = s_src;
   const int o0 = a.obs_off[t], L = a.obs_off[t + 1] - o0, L2 = 2 * L;
   double* Zr = a.Z + (size_t)3 * t * c;
@@ -441,6 +472,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
     }
   }
   __syncthreads();
+  stamp();  // X, r
   // ---- column-pivoted Householder QR of H_f (2L x 3): the trailing 2L-3 columns of Q are A_j (msckf.h:954-955)
   S tau[3];
 #pragma unroll
@@ -494,6 +526,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
     }
     __syncthreads();
   }
+  stamp();  // colpiv QR
   // export v_k, tau for the explicit-row kernel
   for (int e = tid; e < 3 * L2; e += JT) a.Vg[3 * 2 * (size_t)o0 + e] = V[e];
   if (tid < 3) a.taug[3 * t + tid] = tau[tid];
@@ -501,25 +534,27 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   // Q = H_0 H_1 H_2 is orthogonal to 1e-16 whatever the filter precision: G_j = I - U_j U_j^T is an exact projector
   // and the body Gram terms and the explicit rows (k_rows) describe the same H_o.
   double tau64[3];
+  {
+    double vv3[3] = {0.0, 0.0, 0.0};
+    for (int row = tid; row < L2; row += JT)  // v_k is zero above row k
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    double sacc = 0.0;
-    for (int row = k + tid; row < L2; row += JT) { const double vv = (double)V[3 * row + k]; sacc += vv * vv; }
-    const double vtv = block_sum(sacc, redd);
-    tau64[k] = (tau[k] != S(0)) ? 2.0 / vtv : 0.0;
+      for (int k = 0; k < 3; ++k) { const double vv = (double)V[3 * row + k]; vv3[k] += vv * vv; }
+    block_sum3(vv3, redd3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tau64[k] = (tau[k] != S(0)) ? 2.0 / vv3[k] : 0.0;
   }
   // ---- U = Q(:,0:3) = H0 H1 H2 [I3; 0]  (fp64)
   for (int e = tid; e < 3 * L2; e += JT) U[e] = ((e / 3) == (e % 3)) ? 1.0 : 0.0;
   __syncthreads();
 #pragma unroll
   for (int k = 2; k >= 0; --k) {
-    double sd[3];
-    for (int cc = 0; cc < 3; ++cc) {
-      double sacc = 0.0;
-      for (int row = k + tid; row < L2; row += JT) sacc += (double)V[3 * row + k] * U[3 * row + cc];
-      sd[cc] = tau64[k] * block_sum(sacc, redd);
+    double sd[3] = {0.0, 0.0, 0.0};
+    for (int row = k + tid; row < L2; row += JT) {
+      const double vk = (double)V[3 * row + k];
+      sd[0] += vk * U[3 * row]; sd[1] += vk * U[3 * row + 1]; sd[2] += vk * U[3 * row + 2];
     }
-    __syncthreads();
+    block_sum3(sd, redd3);
+    sd[0] *= tau64[k]; sd[1] *= tau64[k]; sd[2] *= tau64[k];
     for (int row = k + tid; row < L2; row += JT) {
       const double vk = (double)V[3 * row + k];
       U[3 * row] -= sd[0] * vk; U[3 * row + 1] -= sd[1] * vk; U[3 * row + 2] -= sd[2] * vk;
@@ -527,13 +562,12 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
     __syncthreads();
   }
   // U^T r in fp64 from the raw residual
-  double urv[3];
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    double sacc = 0.0;
-    for (int row = tid; row < L2; row += JT) sacc += U[3 * row + q] * (double)r[row];
-    urv[q] = block_sum(sacc, redd);
+  double urv[3] = {0.0, 0.0, 0.0};
+  for (int row = tid; row < L2; row += JT) {
+    const double rr = (double)r[row];
+    urv[0] += U[3 * row] * rr; urv[1] += U[3 * row + 1] * rr; urv[2] += U[3 * row + 2] * rr;
   }
+  block_sum3(urv, redd3);
   // ---- r~ = H2 H1 H0 r in the filter precision (r_o = r~[3:], used by the gate only)
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -544,6 +578,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
     for (int row = k + tid; row < L2; row += JT) r[row] -= sdot * V[3 * row + k];
     __syncthreads();
   }
+  stamp();  // U, ur, r~
   // ---- gating (msckf.h:1103-1124): gamma = r_o^T (H_o P H_o^T + u_var I)^-1 r_o with H_o = (Q^T X)[3:]
   // Y = X P_sub X^T, symmetric 2L x 2L, packed lower
   {
@@ -584,16 +619,27 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
     }
   }
   __syncthreads();
+  stamp();  // Y pairs
   // two-sided reflectors: Y <- H_k Y H_k on the trailing (>= k) block
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const S tk = tau[k];
     if (tk != S(0)) {
       for (int ar = k + tid; ar < L2; ar += JT) {
-        S sacc = 0;
-        for (int b = k; b <= ar; ++b) sacc += Y[pk(ar, b)] * V[3 * b + k];
-        for (int b = ar + 1; b < L2; ++b) sacc += Y[pk(b, ar)] * V[3 * b + k];
-        wv[ar] = sacc;
+        S w4[4] = {S(0), S(0), S(0), S(0)};
+        const S* rowa = Y + pk(ar, 0);
+        int b = k;
+        for (; b + 4 <= ar + 1; b += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) w4[u] += rowa[b + u] * V[3 * (b + u) + k];
+        }
+        for (; b <= ar; ++b) w4[0] += rowa[b] * V[3 * b + k];
+        for (b = ar + 1; b + 4 <= L2; b += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) w4[u] += Y[pk(b + u, ar)] * V[3 * (b + u) + k];
+        }
+        for (; b < L2; ++b) w4[0] += Y[pk(b, ar)] * V[3 * b + k];
+        wv[ar] = (w4[0] + w4[1]) + (w4[2] + w4[3]);
       }
       __syncthreads();
       S aacc = 0;
@@ -602,41 +648,52 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
       const S hc = tk * tk * alpha * S(0.5);
       for (int ar = k + tid; ar < L2; ar += JT) pv[ar] = tk * wv[ar] - hc * V[3 * ar + k];
       __syncthreads();
-      const int nk = L2 - k, ntri = nk * (nk + 1) / 2;
-      for (int e = tid; e < ntri; e += JT) {
-        int ia = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        while (ia * (ia + 1) / 2 > e) --ia;
-        while ((ia + 1) * (ia + 2) / 2 <= e) ++ia;
-        const int ib = e - ia * (ia + 1) / 2;
-        const int ar = k + ia, b = k + ib;
-        Y[pk(ar, b)] -= V[3 * ar + k] * pv[b] + pv[ar] * V[3 * b + k];
+      for (int ar = k + (tid >> 5); ar < L2; ar += JT / 32) {  // one row per warp, lanes along the row
+        const S va = V[3 * ar + k], pa = pv[ar];
+        for (int b = k + lane; b <= ar; b += 32) Y[pk(ar, b)] -= va * pv[b] + pa * V[3 * b + k];
       }
       __syncthreads();
     }
   }
-  // S = Y[3:,3:] + u_var I ; Cholesky with the right-hand side r~[3:] carried as an extra row
+  stamp();  // two-sided reflectors
+  // S = Y[3:,3:] + u_var I ; left-looking Cholesky, one matrix row per thread (threads >= rows idle), the right-hand
+  // side r~[3:] rides along as an extra row.  Per column: one dot product over the finished columns (contiguous in the
+  // packed row), the pivot broadcast through shared memory, two barriers.
   const S uvar = st->u_var;
   for (int j = 3 + tid; j < L2; j += JT) Y[pk(j, j)] += uvar;
+  __shared__ S s_piv;
   bool chol_ok = true;
   for (int j = 3; j < L2; ++j) {
     __syncthreads();
-    const S dj = Y[pk(j, j)];
-    if (!(dj > S(0))) { chol_ok = false; break; }
-    const S ljj = tsqrt<S>(dj);
-    const S ej = r[j] / ljj;
-    for (int i = j + 1 + tid; i < L2; i += JT) Y[pk(i, j)] /= ljj;
+    // rows i = j .. L2-1 and the extra row (index L2): strided over the CTA's threads
+    S sv[2] = {S(0), S(0)};
+    int cnt = 0;
+    for (int i = j + tid; i <= L2; i += JT, ++cnt) {
+      const S* rowi = (i < L2) ? (Y + pk(i, 0)) : nullptr;
+      const S* rowj = Y + pk(j, 0);
+      S sacc = (i < L2) ? rowi[j] : r[j];
+      {
+        const S* src = (i < L2) ? rowi : r;  // the extra row is the right-hand side
+        S p4[4] = {S(0), S(0), S(0), S(0)};  // 4 partial sums: short FMA chains, loads issued back to back
+        int cc = 3;
+        for (; cc + 4 <= j; cc += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) p4[u] += src[cc + u] * rowj[cc + u];
+        }
+        for (; cc < j; ++cc) p4[0] += src[cc] * rowj[cc];
+        sacc -= (p4[0] + p4[1]) + (p4[2] + p4[3]);
+      }
+      if (cnt < 2) sv[cnt] = sacc;
+      if (i == j) s_piv = sacc;
+    }
     __syncthreads();
-    if (tid == 0) r[j] = ej;
-    const int nk = L2 - j - 1, ntri = nk * (nk + 1) / 2;
-    for (int e = tid; e < ntri; e += JT) {
-      int ia = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-      while (ia * (ia + 1) / 2 > e) --ia;
-      while ((ia + 1) * (ia + 2) / 2 <= e) ++ia;
-      const int ib = e - ia * (ia + 1) / 2;
-      const int i = j + 1 + ia, cc = j + 1 + ib;
-      const S lij = Y[pk(i, j)];
-      Y[pk(i, cc)] -= lij * Y[pk(cc, j)];
-      if (ib == 0) r[i] -= ej * lij;  // one thread per row carries the right-hand side
+    const S dj = s_piv;
+    if (!(dj > S(0))) { chol_ok = false; break; }
+    const S inv = S(1) / tsqrt<S>(dj);
+    cnt = 0;
+    for (int i = j + tid; i <= L2; i += JT, ++cnt) {
+      const S v = sv[cnt < 2 ? cnt : 1] * inv;
+      if (i < L2) Y[pk(i, j)] = v; else r[j] = v;
     }
   }
   __syncthreads();
@@ -645,6 +702,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   S gam = block_sum(gacc, reds);
   const int acc = chol_ok && (gam < st->chi2[L]);  // table[dof+1], dof = L-1 (msckf.h:433,:1117)
   if (!chol_ok) gam = S(1e30);
+  stamp();  // Cholesky + gamma
   // ---- compact outputs for the Gram stage
   for (int k = tid; k < 3 * c; k += JT) { Zr[k] = 0.0; Yr[k] = 0.0; }
   double Mm[6] = {0, 0, 0, 0, 0, 0};  // M = U^T D U (3x3 symmetric), D = diag(u_var, v_var, u_var, ...)
@@ -684,6 +742,8 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
     a.rows[t] = acc ? (L2 - 3) : 0;
     for (int q = 0; q < 3; ++q) a.ur[3 * t + q] = acc ? urv[q] : 0.0;
   }
+  stamp();  // outputs
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[prof_i] = 0ull;
 }
 
 // Ordered stacking (msckf.h:433-445): exclusive prefix sum of the accepted blocks' row counts.

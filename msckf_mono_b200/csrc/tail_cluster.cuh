@@ -3,7 +3,7 @@
 //     Gamma (Gram matrix of the basis)      -> rank decision        }  rank-revealing Cholesky of Gamma and S''
 //     S'' = L L^T over the kept indices                              }  in lockstep, blocked by NB
 //     W = L^-1 [T''P | r'']                                         (forward substitution, RHS columns sharded)
-//     P <- P - W^T W,   dx = W^T y,  state injection                (msckf.h:1373-1418)
+// followed by  P <- P - W^T W (k_syrk, all SMs) and dx = W^T y + state injection (k_inject)   (msckf.h:1373-1418)
 // The matrices stay in global memory (they are L2 resident: n <= 639, fp64); cluster barriers (release/acquire
 // at cluster scope, ~0.3 us) order the phases, so the O(n^3) trailing updates, the substitutions and the SYRK
 // are spread over the cluster's SMs while the O(n NB^2) diagonal-block factorisations run on CTA 0.
@@ -16,7 +16,7 @@
 namespace mb {
 namespace cg = cooperative_groups;
 
-constexpr int kTailThreads = 512;
+constexpr int kTailThreads = 256;
 
 template <int NB>
 __device__ __forceinline__ void tc_load_diag(double* D, const double* A, int ld, int kb, int nb, int tid) {
@@ -28,30 +28,32 @@ __device__ __forceinline__ void tc_load_diag(double* D, const double* A, int ld,
   }
 }
 
-// one panel row: x D^T = a  (row in registers; dropped columns give 0)
+// one panel row: x D^T = a with the row in registers; inv[] holds 1 / D_jj (0 for dropped columns); the solved row
+// is written transposed into the shared panel PT (and optionally back to global)
 template <int NB>
-__device__ __forceinline__ void tc_panel_row(double* Mx, int ld, int row, int kb, int nb, const double* D, const int* bkeep) {
+__device__ __forceinline__ void tc_panel_row(const double* Mx, int ld, int row, int kb, int nb, const double* D, const double* inv,
+                                             double* PT, int ldt, int prow, double* Lw /*nullable: where the solved row goes*/) {
   constexpr int LD = NB + 1;
   double x[NB];
 #pragma unroll
   for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? Mx[(size_t)row * ld + kb + j] : 0.0;
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    double v = x[j];
+  for (int j = 0; j < NB; ++j) {  // right-looking: the updates of the later entries are independent (full ILP)
+    x[j] *= inv[j];
 #pragma unroll
-    for (int cc = 0; cc < j; ++cc) v -= x[cc] * D[j * LD + cc];
-    x[j] = ((j < nb) && bkeep[j]) ? v / D[j * LD + j] : 0.0;
+    for (int jj = j + 1; jj < NB; ++jj) x[jj] -= x[j] * D[jj * LD + j];
   }
 #pragma unroll
-  for (int j = 0; j < NB; ++j)
-    if (j < nb) Mx[(size_t)row * ld + kb + j] = x[j];
+  for (int j = 0; j < NB; ++j) {
+    PT[(size_t)j * ldt + prow] = x[j];
+    if (Lw && j < nb) Lw[(size_t)row * ld + kb + j] = x[j];
+  }
 }
 
-// C[4][4] += sum_j At[j][ra..ra+3] * Bt[j][rb..rb+3] over the NB panel columns (transposed panels, row stride ldt)
-template <int NB>
-__device__ __forceinline__ void tc_tile_4x4(const double* At, const double* Bt, int ldt, int ra, int rb, double acc[4][4]) {
+// C[4][4] += sum_j At[j][ra..ra+3] * Bt[j][rb..rb+3] over nk rows of the (transposed) operands, row stride ldt
+__device__ __forceinline__ void tc_tile_4x4(const double* At, const double* Bt, int ldt, int ra, int rb, int nk, double acc[4][4]) {
 #pragma unroll 4
-  for (int j = 0; j < NB; ++j) {
+  for (int j = 0; j < nk; ++j) {
     const double2 a01 = *reinterpret_cast<const double2*>(At + (size_t)j * ldt + ra);
     const double2 a23 = *reinterpret_cast<const double2*>(At + (size_t)j * ldt + ra + 2);
     const double2 b01 = *reinterpret_cast<const double2*>(Bt + (size_t)j * ldt + rb);
@@ -64,14 +66,23 @@ __device__ __forceinline__ void tc_tile_4x4(const double* At, const double* Bt, 
   }
 }
 
+__device__ __forceinline__ void tc_tile_index(int tl, int& ti, int& tj) {  // tl -> (ti >= tj) of the lower triangle
+  ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
+  while (ti * (ti + 1) / 2 > tl) --ti;
+  while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+  tj = tl - ti * (ti + 1) / 2;
+}
+
 template <class S, int NB>
 __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, const double* __restrict__ T2, double* __restrict__ G,
-                                                      double* __restrict__ A, int* __restrict__ keep, double thr,
-                                                      int* __restrict__ rank_out, const int* __restrict__ m_in,
+                                                      double* __restrict__ A, double* __restrict__ Lout, int* __restrict__ keep,
+                                                      double* __restrict__ idiag,
+                                                      double thr, int* __restrict__ rank_out, const int* __restrict__ m_in,
                                                       const double* __restrict__ TP, const double* __restrict__ r2,
                                                       double* __restrict__ Wm, double* __restrict__ yv, S* __restrict__ P, int ldp,
                                                       DevState<S>* st, S* __restrict__ poses, double* __restrict__ dx_out,
                                                       unsigned long long* __restrict__ prof /*optional phase timestamps*/) {
+  static_assert(NB <= 32, "the diagonal block is factorised by one warp, one row per lane");
   cg::cluster_group cluster = cg::this_cluster();
   int prof_i = 0;
   auto stamp = [&]() {
@@ -84,17 +95,17 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
   stamp();
   const int crank = (int)cluster.block_rank();
   const int C = (int)cluster.num_blocks();
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int LD = NB + 1;
   extern __shared__ __align__(16) double sm[];
-  const int ldt = (n + 3) & ~3;              // transposed-panel row stride (16-byte aligned rows)
+  const int ldt = (n + 3) & ~3;              // row stride of the transposed panels (16-byte aligned rows)
   double* DG = sm;                           // [NB][LD]
   double* DA = DG + NB * LD;                 // [NB][LD]
-  double* PT_A = DA + NB * LD + ((NB * LD) & 1);  // [NB][ldt]  panel of A, transposed  (also W slab / SYRK tiles later)
-  double* PT_G = PT_A + (size_t)NB * ldt;    // [NB][ldt]  panel of G, transposed
-  double* d0 = PT_G + (size_t)NB * ldt;      // [n] original diagonal of Gamma (CTA 0)
-  int* bkeep = reinterpret_cast<int*>(d0 + ((n + 1) & ~1));  // [NB] keep flags of the current block
-  __shared__ double dgk[NB], dak[NB];
+  double* PT_A = DA + NB * LD + ((NB * LD) & 1);  // [NB][ldt]  panel of A, transposed (later: W slab, W k-blocks)
+  double* PT_G = PT_A + (size_t)NB * ldt;    // [NB][ldt]  panel of G, transposed (later: L panel, dx)
+  double* d0 = PT_G + (size_t)NB * ldt;      // [n] original diagonal of Gamma (CTA 0); later keep flags
+  double* idg = d0 + ((n + 1) & ~1);         // [NB] 1 / diag of the current block of G's factor (0 = dropped)
+  double* ida = idg + NB;                    // [NB] same for A
   __shared__ int s_rank;
   const int m = *m_in;
   const bool full = m <= n;  // all rows explicit and orthonormal: Gamma = I_m, nothing to decide, G untouched
@@ -120,7 +131,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
     }
   }
   cluster.sync();
-  stamp();  // [1] gamma built
+  stamp();  // Gamma built
   if (crank == 0) {
     for (int k = tid; k < n; k += kTailThreads) d0[k] = full ? (k < m ? 1.0 : 0.0) : G[(size_t)k * ld + k];
     if (tid == 0) s_rank = 0;
@@ -130,70 +141,74 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
   for (int kb = 0; kb < n; kb += NB) {
     const int nb = min(NB, n - kb);
     const int r0 = kb + nb;
-    // phase 1 (CTA 0): diagonal blocks
+    // phase 1 (CTA 0): diagonal blocks, one warp, lane = row, both matrices interleaved, no divisions (rsqrt)
     if (crank == 0) {
       if (!full) tc_load_diag<NB>(DG, G, ld, kb, nb, tid);
       tc_load_diag<NB>(DA, A, ld, kb, nb, tid);
-      int rank_now = s_rank;
-      for (int k = 0; k < nb; ++k) {
-        __syncthreads();
-        const double pg = full ? 1.0 : DG[k * LD + k], pa = DA[k * LD + k], dk0 = d0[kb + k];
-        const bool drop = !(dk0 > 0.0) || !(pg > thr * dk0) || rank_now >= rank_cap || !(pa > 0.0);
-        if (!drop) rank_now++;
-        double lg = 1.0, la = 1.0;
-        if (tid < 32 && !drop) { lg = sqrt(pg); la = sqrt(pa); }   // one warp computes the roots ...
-        if (tid == 0) { dgk[k] = lg; dak[k] = la; bkeep[k] = drop ? 0 : 1; }
-        __syncthreads();                                         // ... everybody reads them
-        lg = dgk[k]; la = dak[k];
-        for (int i = k + 1 + tid; i < nb; i += kTailThreads) {
-          if (drop) { DA[i * LD + k] = 0.0; if (!full) DG[i * LD + k] = 0.0; }
-          else { DA[i * LD + k] /= la; if (!full) DG[i * LD + k] /= lg; }
-        }
-        if (drop)
-          for (int j = tid; j < k; j += kTailThreads) { DA[k * LD + j] = 0.0; if (!full) DG[k * LD + j] = 0.0; }
-        __syncthreads();
-        if (!drop) {
-          const int rem = nb - k - 1;
-          for (int e = tid; e < rem * rem; e += kTailThreads) {
-            const int i = k + 1 + e / rem, j = k + 1 + e % rem;
-            if (j <= i) {
-              DA[i * LD + j] -= DA[i * LD + k] * DA[j * LD + k];
-              if (!full) DG[i * LD + j] -= DG[i * LD + k] * DG[j * LD + k];
-            }
-          }
-        }
-      }
       __syncthreads();
-      if (tid == 0) s_rank = rank_now;
-      if (tid < nb) { DG[tid * LD + tid] = dgk[tid]; DA[tid * LD + tid] = dak[tid]; keep[kb + tid] = bkeep[tid]; }
+      if (warp == 0) {
+        int rank_now = s_rank;
+        for (int k = 0; k < nb; ++k) {
+          // left-looking: column k of both factors from the already final columns j < k (reads only, no RMW chain)
+          double sa = 0.0, sg = 0.0;
+          if (lane >= k && lane < nb) {
+            sa = DA[lane * LD + k];
+            if (!full) sg = DG[lane * LD + k];
+            double a4[4] = {0.0, 0.0, 0.0, 0.0}, g4[4] = {0.0, 0.0, 0.0, 0.0};  // 4 partial sums: short FMA chains
+            int j = 0;
+            for (; j + 4 <= k; j += 4) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                a4[u] += DA[lane * LD + j + u] * DA[k * LD + j + u];
+                if (!full) g4[u] += DG[lane * LD + j + u] * DG[k * LD + j + u];
+              }
+            }
+            for (; j < k; ++j) { a4[0] += DA[lane * LD + j] * DA[k * LD + j]; if (!full) g4[0] += DG[lane * LD + j] * DG[k * LD + j]; }
+            sa -= (a4[0] + a4[1]) + (a4[2] + a4[3]);
+            sg -= (g4[0] + g4[1]) + (g4[2] + g4[3]);
+          }
+          const double pa = __shfl_sync(0xffffffffu, sa, k), pg = full ? 1.0 : __shfl_sync(0xffffffffu, sg, k);
+          const double dk0 = d0[kb + k];
+          const bool drop = !(dk0 > 0.0) || !(pg > thr * dk0) || rank_now >= rank_cap || !(pa > 0.0);
+          if (!drop) rank_now++;
+          const double ig = drop ? 0.0 : rsqrt(pg), ia = drop ? 0.0 : rsqrt(pa);
+          __syncwarp();
+          if (lane > k && lane < nb) { DA[lane * LD + k] = sa * ia; if (!full) DG[lane * LD + k] = sg * ig; }
+          if (lane == k) {
+            DA[k * LD + k] = drop ? 1.0 : pa * ia; DG[k * LD + k] = drop ? 1.0 : pg * ig;
+            ida[k] = ia; idg[k] = ig;
+          }
+          if (drop && lane < k) { DA[k * LD + lane] = 0.0; DG[k * LD + lane] = 0.0; }
+          __syncwarp();
+        }
+        if (lane == 0) s_rank = rank_now;
+        for (int k = nb + lane; k < NB; k += 32) { ida[k] = 0.0; idg[k] = 0.0; }
+      }
       __syncthreads();
       for (int e = tid; e < nb * nb; e += kTailThreads) {
         const int i = e / nb, j = e % nb;
-        if (j <= i) { A[(size_t)(kb + i) * ld + kb + j] = DA[i * LD + j]; if (!full) G[(size_t)(kb + i) * ld + kb + j] = DG[i * LD + j]; }
+        if (j <= i) {
+          A[(size_t)(kb + i) * ld + kb + j] = DA[i * LD + j];     // read by the other CTAs in phase 2
+          Lout[(size_t)(kb + i) * ld + kb + j] = DA[i * LD + j];  // the factor itself (A's panels stay untouched: they are
+          if (!full) G[(size_t)(kb + i) * ld + kb + j] = DG[i * LD + j];  // being read concurrently by the whole cluster)
+        }
       }
+      if (tid < nb) { keep[kb + tid] = ida[tid] != 0.0 ? 1 : 0; idiag[kb + tid] = ida[tid]; idiag[n + kb + tid] = idg[tid]; }
     }
-    stamp();  // diag block done (CTA 0)
+    stamp();  // diagonal block done
     if (r0 >= n) break;  // last block: nothing below
     cluster.sync();
-    // phase 2 (all CTAs): panel rows below the block, one row per thread
+    // phase 2 (every CTA, redundantly): all panel rows below the block -> transposed shared panel (CTA 0 also -> global)
     if (crank != 0) {
       if (!full) tc_load_diag<NB>(DG, G, ld, kb, nb, tid);
       tc_load_diag<NB>(DA, A, ld, kb, nb, tid);
-      if (tid < NB) bkeep[tid] = (tid < nb) ? keep[kb + tid] : 0;
+      if (tid < NB) { ida[tid] = (tid < nb) ? idiag[kb + tid] : 0.0; idg[tid] = (tid < nb) ? idiag[n + kb + tid] : 0.0; }
     }
     __syncthreads();
-    for (int row = r0 + gtid; row < n; row += gthreads) {
-      tc_panel_row<NB>(A, ld, row, kb, nb, DA, bkeep);
-      if (!full) tc_panel_row<NB>(G, ld, row, kb, nb, DG, bkeep);
-    }
-    cluster.sync();
-    stamp();  // panel done
-    // phase 3 (all CTAs): trailing update, 4x4 register tiles on the transposed panel
     const int nr = n - r0;
-    for (int e = tid; e < nr * NB; e += kTailThreads) {
-      const int i = e / NB, j = e % NB;
-      PT_A[(size_t)j * ldt + i] = (j < nb) ? A[(size_t)(r0 + i) * ld + kb + j] : 0.0;
-      if (!full) PT_G[(size_t)j * ldt + i] = (j < nb) ? G[(size_t)(r0 + i) * ld + kb + j] : 0.0;
+    for (int row = r0 + tid; row < n; row += kTailThreads) {
+      tc_panel_row<NB>(A, ld, row, kb, nb, DA, ida, PT_A, ldt, row - r0, crank == 0 ? Lout : nullptr);
+      if (!full) tc_panel_row<NB>(G, ld, row, kb, nb, DG, idg, PT_G, ldt, row - r0, nullptr);
     }
     {  // zero the tail of the padded rows so that partial tiles read zeros
       const int nrp = (nr + 3) & ~3;
@@ -204,14 +219,14 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
       }
     }
     __syncthreads();
+    stamp();  // panel done
+    // phase 3 (cluster-wide): trailing update, 4x4 register tiles on the transposed panel
     const int nt = (nr + 3) / 4, ntile = nt * (nt + 1) / 2;
     for (int tl = gtid; tl < ntile; tl += gthreads) {
-      int ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
-      while (ti * (ti + 1) / 2 > tl) --ti;
-      while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
-      const int tj = tl - ti * (ti + 1) / 2;
+      int ti, tj;
+      tc_tile_index(tl, ti, tj);
       double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-      tc_tile_4x4<NB>(PT_A, PT_A, ldt, 4 * ti, 4 * tj, acc);
+      tc_tile_4x4(PT_A, PT_A, ldt, 4 * ti, 4 * tj, NB, acc);
 #pragma unroll
       for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -221,7 +236,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
         }
       if (!full) {
         double acg[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-        tc_tile_4x4<NB>(PT_G, PT_G, ldt, 4 * ti, 4 * tj, acg);
+        tc_tile_4x4(PT_G, PT_G, ldt, 4 * ti, 4 * tj, NB, acg);
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -231,28 +246,27 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
           }
       }
     }
+    stamp();  // trailing computed (CTA 0)
     cluster.sync();
     stamp();  // trailing done
   }
   cluster.sync();
-  if (gtid == 0) *rank_out = s_rank;  // CTA 0 thread 0 (gtid 0) owns s_rank
+  if (gtid == 0) *rank_out = s_rank;
   // dropped rows: clear what earlier panels wrote left of the diagonal
   for (size_t e = gtid; e < (size_t)n * n; e += gthreads) {
     const int k = (int)(e / n), cc = (int)(e % n);
-    if (cc < k && !keep[k]) A[(size_t)k * ld + cc] = 0.0;
+    if (cc < k && !keep[k]) Lout[(size_t)k * ld + cc] = 0.0;
   }
   cluster.sync();
   stamp();  // factorisation complete
   // ---------------------------------------------------------------- W = L^-1 [TP | r''], RHS columns sharded over the cluster
   {
     const int ncol = n + 1;
-    // columns per chunk: an even share of the RHS, bounded by what fits in the (now free) panel buffers
-    const int cwmax = max(1, min(kTailThreads, (int)((2 * (size_t)NB * ldt) / (size_t)n)));
-    const int per = min(cwmax, (ncol + C - 1) / C);
+    const int per = max(1, min(NB, (ncol + C - 1) / C));  // columns per chunk: Ws [n][per] fits the A-panel buffer
     const int nchunk = (ncol + per - 1) / per;
-    double* Ws = PT_A;                       // [n][per]
-    double* Dblk = DG;
-    int* skeep = reinterpret_cast<int*>(d0); // reuse
+    double* Ws = PT_A;                        // [n][per]
+    double* Lp = PT_G;                        // [n - r0][NB] panel of L below the current block
+    int* skeep = reinterpret_cast<int*>(d0);  // [n]
     for (int k = tid; k < n; k += kTailThreads) skeep[k] = keep[k];
     for (int q = crank; q < nchunk; q += C) {
       const int col0 = q * per, cw = min(per, ncol - col0);
@@ -263,35 +277,47 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
         if (skeep[row]) v = (col < n) ? TP[(size_t)row * ld + col] : r2[row];
         Ws[(size_t)row * per + cc] = v;
       }
+      const int rgs = kTailThreads / cw;  // row groups for the update
+      const int ucc = tid % cw, urg = tid / cw;
       for (int kb = 0; kb < n; kb += NB) {
         const int nb = min(NB, n - kb), r0 = kb + nb;
         __syncthreads();
-        tc_load_diag<NB>(Dblk, A, ld, kb, nb, tid);
-        __syncthreads();
-        if (tid < cw) {
-          double x[NB];
-#pragma unroll
-          for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? Ws[(size_t)(kb + j) * per + tid] : 0.0;
-#pragma unroll
-          for (int j = 0; j < NB; ++j) {
-            double v = x[j];
-#pragma unroll
-            for (int cc = 0; cc < j; ++cc) v -= Dblk[j * LD + cc] * x[cc];
-            x[j] = ((j < nb) && skeep[kb + j]) ? v / Dblk[j * LD + j] : 0.0;
-          }
-#pragma unroll
-          for (int j = 0; j < NB; ++j)
-            if (j < nb) Ws[(size_t)(kb + j) * per + tid] = x[j];
+        tc_load_diag<NB>(DA, Lout, ld, kb, nb, tid);
+        if (tid < NB) ida[tid] = (tid < nb) ? idiag[kb + tid] : 0.0;
+        for (int e = tid; e < (n - r0) * NB; e += kTailThreads) {  // coalesced panel load
+          const int i = e / NB, j = e % NB;
+          Lp[(size_t)i * NB + j] = (j < nb) ? Lout[(size_t)(r0 + i) * ld + kb + j] : 0.0;
         }
         __syncthreads();
-        // rows below: Ws[r][c] -= sum_j L[r][kb+j] * Ws[kb+j][c]   (L rows from global/L2, broadcast within a warp)
-        for (int e = tid; e < (n - r0) * cw; e += kTailThreads) {
-          const int i = e / cw, cc = e % cw;
-          const double* lrow = A + (size_t)(r0 + i) * ld + kb;
-          double s = 0.0;
-#pragma unroll 8
-          for (int j = 0; j < nb; ++j) s += lrow[j] * Ws[(size_t)(kb + j) * per + cc];
-          Ws[(size_t)(r0 + i) * per + cc] -= s;
+        double x[NB];
+        if (urg < rgs) {
+          // every row group solves the diagonal block for its column redundantly (registers), then updates its rows
+#pragma unroll
+          for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? Ws[(size_t)(kb + j) * per + ucc] : 0.0;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            x[j] *= ida[j];
+#pragma unroll
+            for (int jj = j + 1; jj < NB; ++jj) x[jj] -= x[j] * DA[jj * LD + j];
+          }
+        }
+        __syncthreads();  // everybody has read the old block rows
+        if (urg < rgs) {
+          if (urg == 0) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              if (j < nb) Ws[(size_t)(kb + j) * per + ucc] = x[j];
+          }
+          for (int i = urg; i < n - r0; i += rgs) {
+            const double* lrow = Lp + (size_t)i * NB;
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NB; j += 2) {
+              const double2 l2 = *reinterpret_cast<const double2*>(lrow + j);
+              s += l2.x * x[j] + l2.y * x[j + 1];
+            }
+            Ws[(size_t)(r0 + i) * per + ucc] -= s;
+          }
         }
       }
       __syncthreads();
@@ -302,93 +328,72 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
       }
     }
   }
-  cluster.sync();
-  stamp();  // substitution complete
-  // ---------------------------------------------------------------- P <- P - W^T W (4x4 register tiles straight from L2), dx = W^T y
-  {
-    const int nt = (n + 3) / 4, ntile = nt * (nt + 1) / 2;
-    for (int tl = gtid; tl < ntile; tl += gthreads) {
-      int ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
-      while (ti * (ti + 1) / 2 > tl) --ti;
-      while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
-      const int tj = tl - ti * (ti + 1) / 2;
-      double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-      for (int k = 0; k < n; ++k) {
-        const double* wr = Wm + (size_t)k * ld;
-        double a[4], b[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) { a[p] = (4 * ti + p < n) ? wr[4 * ti + p] : 0.0; b[p] = (4 * tj + p < n) ? wr[4 * tj + p] : 0.0; }
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[p][q] += a[p] * b[q];
-      }
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int a_ = 4 * ti + p, b_ = 4 * tj + q;
-          if (a_ < n && b_ < n && b_ <= a_) {
-            const S v = (S)((double)P[(size_t)a_ * ldp + b_] - acc[p][q]);
-            P[(size_t)a_ * ldp + b_] = v;
-            P[(size_t)b_ * ldp + a_] = v;  // exactly symmetric by construction
-          }
-        }
-    }
+  stamp();  // substitution complete (this CTA)
+  stamp();  // end
+  if (prof && blockIdx.x == 0 && threadIdx.x == 0 && prof_i < 64) prof[prof_i] = 0ull;
+}
+
+
+// dx = W^T y, then the state correction of msckf.h:1373-1391.  Single CTA.
+template <class S>
+__global__ void __launch_bounds__(1024) k_inject(int n, int ld, int M, const double* __restrict__ Wm, const double* __restrict__ yv,
+                                                DevState<S>* st, S* __restrict__ poses, double* __restrict__ dx_out,
+                                                const int* __restrict__ m_in, const int* __restrict__ rank_in) {
+  extern __shared__ double sdx[];
+  const int tid = threadIdx.x;
+  if (*m_in == 0) {  // nothing accepted: the reference returns before touching the state (msckf.h:401-403,:1328)
+    for (int a = tid; a < n; a += 1024) dx_out[a] = 0.0;
+    return;
   }
-  stamp();  // syrk (CTA 0's share) done
-  if (crank == 0) {  // dx = W^T y and the state injection (msckf.h:1373-1391)
-    double* sdx = PT_G;  // [n]
-    __shared__ double part[16][33];
-    const int al = tid & 31, kg = tid >> 5;  // 32 columns x 16 k-groups
+  {
+    __shared__ double part[32][33];
+    const int al = tid & 31, kg = tid >> 5;
     for (int a0 = 0; a0 < n; a0 += 32) {
       const int a = a0 + al;
       double s = 0.0;
       if (a < n)
-        for (int k = kg; k < n; k += 16) s += Wm[(size_t)k * ld + a] * yv[k];
+        for (int k = kg; k < n; k += 32) s += Wm[(size_t)k * ld + a] * yv[k];
       part[kg][al] = s;
       __syncthreads();
       if (kg == 0 && a < n) {
         double t = 0.0;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) t += part[g][al];
+        for (int g = 0; g < 32; ++g) t += part[g][al];
         sdx[a] = t;
         dx_out[a] = t;
       }
       __syncthreads();
     }
-    if (tid == 0) {
-      const S dth[3] = {(S)sdx[0], (S)sdx[1], (S)sdx[2]};
-      S uq[4], qn[4];
-      build_update_quat(dth, uq);
-      quat_mul(uq, st->q_IG, qn);  // not renormalised (msckf.h:1376-1378)
-      for (int i = 0; i < 4; ++i) st->q_IG[i] = qn[i];
-      for (int i = 0; i < 3; ++i) {
-        st->b_g[i] += (S)sdx[3 + i];
-        st->v_I_G[i] += (S)sdx[6 + i];
-        st->b_a[i] += (S)sdx[9 + i];
-        st->p_I_G[i] += (S)sdx[12 + i];
-      }
-      st->n_updates += 1;
-      st->last_m = m;
-      st->last_rank = s_rank;
-      double nn = 0.0;
-      for (int a = 0; a < n; ++a) nn += sdx[a] * sdx[a];
-      st->last_dx_norm = sqrt(nn);
-    }
-    for (int ci = tid; ci < M; ci += kTailThreads) {
-      S* ps = poses + kPoseStride * ci;
-      const S dth[3] = {(S)sdx[15 + 6 * ci], (S)sdx[16 + 6 * ci], (S)sdx[17 + 6 * ci]};
-      S uq[4], qn[4];
-      build_update_quat(dth, uq);
-      quat_mul(uq, ps, qn);
-      quat_normalize(qn);
-      ps[0] = qn[0]; ps[1] = qn[1]; ps[2] = qn[2]; ps[3] = qn[3];
-      ps[4] += (S)sdx[18 + 6 * ci]; ps[5] += (S)sdx[19 + 6 * ci]; ps[6] += (S)sdx[20 + 6 * ci];
-    }
   }
-  stamp();  // end
-  if (prof && blockIdx.x == 0 && threadIdx.x == 0 && prof_i < 64) prof[prof_i] = 0ull;
+  if (tid == 0) {
+    const S dth[3] = {(S)sdx[0], (S)sdx[1], (S)sdx[2]};
+    S uq[4], qn[4];
+    build_update_quat(dth, uq);
+    quat_mul(uq, st->q_IG, qn);  // not renormalised (msckf.h:1376-1378)
+    for (int i = 0; i < 4; ++i) st->q_IG[i] = qn[i];
+    for (int i = 0; i < 3; ++i) {
+      st->b_g[i] += (S)sdx[3 + i];
+      st->v_I_G[i] += (S)sdx[6 + i];
+      st->b_a[i] += (S)sdx[9 + i];
+      st->p_I_G[i] += (S)sdx[12 + i];
+    }
+    st->n_updates += 1;
+    st->last_m = *m_in;
+    st->last_rank = *rank_in;
+    double nn = 0.0;
+    for (int a = 0; a < n; ++a) nn += sdx[a] * sdx[a];
+    st->last_dx_norm = sqrt(nn);
+  }
+  for (int ci = tid; ci < M; ci += 1024) {
+    S* ps = poses + kPoseStride * ci;
+    const S dth[3] = {(S)sdx[15 + 6 * ci], (S)sdx[16 + 6 * ci], (S)sdx[17 + 6 * ci]};
+    S uq[4], qn[4];
+    build_update_quat(dth, uq);
+    quat_mul(uq, ps, qn);
+    quat_normalize(qn);
+    ps[0] = qn[0]; ps[1] = qn[1]; ps[2] = qn[2]; ps[3] = qn[3];
+    ps[4] += (S)sdx[18 + 6 * ci]; ps[5] += (S)sdx[19 + 6 * ci]; ps[6] += (S)sdx[20 + 6 * ci];
+  }
 }
 
 }  // namespace mb

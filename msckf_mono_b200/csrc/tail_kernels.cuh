@@ -8,71 +8,94 @@
 
 namespace mb {
 
-// TP[a][b] = sum_k T2[a][k] * P[k][b]      (T2 columns < 15 are zero)
-template <class S>
-__global__ void __launch_bounds__(256) k_gemm_tp(int n, int ld, const double* __restrict__ T2, const S* __restrict__ P, int ldp,
-                                                double* __restrict__ TP) {
-  __shared__ double sA[32][17], sB[16][33];
-  const int ta = blockIdx.y * 32, tb = blockIdx.x * 32;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[2][2] = {{0, 0}, {0, 0}};
-  for (int kb = kImuDim; kb < n; kb += 16) {
-    for (int e = threadIdx.x; e < 32 * 16; e += 256) {
-      const int r = e / 16, kk = e % 16;
-      const int a = ta + r, k = kb + kk;
-      sA[r][kk] = (a < n && k < n) ? T2[(size_t)a * ld + k] : 0.0;
+// One 32 x 32 output tile per CTA of 64 threads (4 x 4 register tile per thread), operands streamed through shared
+// memory in 32-deep k-slabs with the next slab prefetched into registers while the current one is multiplied:
+// at n <= 639 these products are bound by the L2 round trip per slab, not by the fp64 pipe, so small tiles
+// (many CTAs) and prefetching are what matters.  LA(k, a) / LB(k, b) fetch operand elements, EPI(a, b, acc) stores.
+template <class LoadA, class LoadB, class Epi>
+__device__ __forceinline__ void gemm_tile32(int n, int k_begin, int a0, int b0, LoadA LA, LoadB LB, Epi EPI) {
+  __shared__ __align__(16) double sA[32][32], sB[32][32];
+  const int tid = threadIdx.x;       // 64 threads
+  const int tx = tid & 7, ty = tid >> 3;
+  double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+  double pa[16], pb[16];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 64 * u, kk = e >> 5, cc = e & 31;
+      const int k = k0 + kk;
+      pa[u] = (k < n && a0 + cc < n) ? LA(k, a0 + cc) : 0.0;
+      pb[u] = (k < n && b0 + cc < n) ? LB(k, b0 + cc) : 0.0;
     }
-    for (int e = threadIdx.x; e < 16 * 32; e += 256) {
-      const int kk = e / 32, cc = e % 32;
-      const int k = kb + kk, b = tb + cc;
-      sB[kk][cc] = (k < n && b < n) ? (double)P[(size_t)k * ldp + b] : 0.0;
-    }
+  };
+  fetch(k_begin);
+  for (int k0 = k_begin; k0 < n; k0 += 32) {
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      const double a0 = sA[ty][kk], a1 = sA[ty + 16][kk], b0 = sB[kk][tx], b1 = sB[kk][tx + 16];
-      acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 64 * u, kk = e >> 5, cc = e & 31;
+      sA[kk][cc] = pa[u];
+      sB[kk][cc] = pb[u];
     }
     __syncthreads();
+    if (k0 + 32 < n) fetch(k0 + 32);
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&sA[kk][4 * ty]), a23 = *reinterpret_cast<const double2*>(&sA[kk][4 * ty + 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&sB[kk][4 * tx]), b23 = *reinterpret_cast<const double2*>(&sB[kk][4 * tx + 2]);
+      const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] += a[p] * b[q];
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int a = ta + ty + 16 * i, b = tb + tx + 16 * j;
-      if (a < n && b < n) TP[(size_t)a * ld + b] = acc[i][j];
+    for (int q = 0; q < 4; ++q) {
+      const int a = a0 + 4 * ty + p, b = b0 + 4 * tx + q;
+      if (a < n && b < n) EPI(a, b, acc[p][q]);
     }
 }
 
+// TP[a][b] = sum_k T2[a][k] * P[k][b]      (T2 columns < 15 are zero)
+template <class S>
+__global__ void __launch_bounds__(64) k_gemm_tp(int n, int ld, const double* __restrict__ T2, const S* __restrict__ P, int ldp,
+                                               double* __restrict__ TP) {
+  gemm_tile32(n, kImuDim, blockIdx.y * 32, blockIdx.x * 32,
+              [&](int k, int a) { return T2[(size_t)a * ld + k]; },
+              [&](int k, int b) { return (double)P[(size_t)k * ldp + b]; },
+              [&](int a, int b, double v) { TP[(size_t)a * ld + b] = v; });
+}
+
 // S2[a][b] = sum_k TP[a][k] * T2[b][k] + R2[a][b]
-__global__ void __launch_bounds__(256) k_gemm_s(int n, int ld, const double* __restrict__ TP, const double* __restrict__ T2,
-                                               const double* __restrict__ R2, double* __restrict__ S2) {
-  __shared__ double sA[32][17], sB[32][17];
-  const int ta = blockIdx.y * 32, tb = blockIdx.x * 32;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[2][2] = {{0, 0}, {0, 0}};
-  for (int kb = kImuDim; kb < n; kb += 16) {
-    for (int e = threadIdx.x; e < 32 * 16; e += 256) {
-      const int r = e / 16, kk = e % 16;
-      const int k = kb + kk;
-      sA[r][kk] = (ta + r < n && k < n) ? TP[(size_t)(ta + r) * ld + k] : 0.0;
-      sB[r][kk] = (tb + r < n && k < n) ? T2[(size_t)(tb + r) * ld + k] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      const double a0 = sA[ty][kk], a1 = sA[ty + 16][kk], b0 = sB[tx][kk], b1 = sB[tx + 16][kk];
-      acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int a = ta + ty + 16 * i, b = tb + tx + 16 * j;
-      if (a < n && b < n) S2[(size_t)a * ld + b] = acc[i][j] + R2[(size_t)a * ld + b];
-    }
+__global__ void __launch_bounds__(64) k_gemm_s(int n, int ld, const double* __restrict__ TP, const double* __restrict__ T2,
+                                              const double* __restrict__ R2, double* __restrict__ S2) {
+  gemm_tile32(n, kImuDim, blockIdx.y * 32, blockIdx.x * 32,  // T2 columns < 15 are zero
+              [&](int k, int a) { return TP[(size_t)a * ld + k]; },
+              [&](int k, int b) { return T2[(size_t)b * ld + k]; },
+              [&](int a, int b, double v) { S2[(size_t)a * ld + b] = v + R2[(size_t)a * ld + b]; });
+}
+
+// P <- P - W^T W (lower-triangular tile pairs; written in the filter precision, exactly symmetric by construction)
+template <class S>
+__global__ void __launch_bounds__(64) k_syrk(int n, int ld, const double* __restrict__ Wm, S* __restrict__ P, int ldp,
+                                            const int* __restrict__ m_in) {
+  if (*m_in == 0) return;
+  int pidx = blockIdx.x, ta = 0;
+  while (pidx >= ta + 1) { pidx -= ta + 1; ++ta; }  // (ta >= tb)
+  const int tb = pidx;
+  gemm_tile32(n, 0, ta * 32, tb * 32,
+              [&](int k, int a) { return Wm[(size_t)k * ld + a]; },
+              [&](int k, int b) { return Wm[(size_t)k * ld + b]; },
+              [&](int a, int b, double v) {
+                if (b <= a) {
+                  const S r = (S)((double)P[(size_t)a * ldp + b] - v);
+                  P[(size_t)a * ldp + b] = r;
+                  P[(size_t)b * ldp + a] = r;
+                }
+              });
 }
 
 }  // namespace mb

@@ -137,7 +137,10 @@ def run_reference(args, rank, world):
     all cores (one update per core per step)."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    # the oracle's working set (three 17100 x 195 matrices per filter) makes it memory-bandwidth bound: throughput
+    # saturates around 16 concurrent filters (measured on the 128-core GPU box: 8.1/s with 128 threads vs 2.0/s with 1),
+    # and a step must stay bounded, so a step = one update on each of min(cores, 16) threads
+    cores = min(os.cpu_count() or 1, 16)
     from concurrent.futures import ThreadPoolExecutor
     from msckf_mono_b200 import synth
     from msckf_mono_b200.cview import CFilter
@@ -199,7 +202,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from msckf_mono_b200 import capi
+    from msckf_mono_b200 import capi, shard
 
     K, W = args.steps, args.warmup
     # ---------------------------------------------------------------- setup (untimed)
@@ -224,8 +227,7 @@ def main():
         return ms, rep
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        shard.barrier()
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- device-timed steps
@@ -281,6 +283,20 @@ def main():
         dt = time.perf_counter() - t0
         if r >= 1:
             batched_s.append(dt)
+    # 32 filters in flight (2 rounds, the first warms up)
+    B2 = 32
+    b2filts = [ready_filter(DTYPE, seq=9000 + rank * 1000 + i, device=local_rank) for i in range(B2 * 2)]
+    batched2_s = []
+    for r in range(2):
+        grp = b2filts[r * B2:(r + 1) * B2]
+        flush_l2()
+        t0 = time.perf_counter()
+        for f in grp:
+            f.marginalizeLaunch()
+        for f in grp:
+            f.marginalizeCollect()
+        if r >= 1:
+            batched2_s.append(time.perf_counter() - t0)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     # ---------------------------------------------------------------- per-kernel profile (CUDA events between kernels)
@@ -307,12 +323,7 @@ def main():
     dom = max(kern_ms, key=kern_ms.get)
 
     # ---------------------------------------------------------------- reduce over ranks
-    if world > 1:
-        t = torch.tensor([dev_ms, e2e_s, float(np.sum(batched_s))], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, bsum = [float(x) for x in t.tolist()]
-    else:
-        bsum = float(np.sum(batched_s))
+    dev_ms, e2e_s, bsum, b2sum = shard.max_over_ranks([dev_ms, e2e_s, float(np.sum(batched_s)), float(np.sum(batched2_s))], device="cuda")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -359,7 +370,8 @@ def main():
                          "sample": f"{cpu_n} marginalize() calls of the same {N_FEAT}x{N_CLONES} fp32 workload in {cpu_wall:.1f} s, "
                                    "oracle/ (CPU restatement of the reference's Eigen path, thin-Q form), single thread like the reference"},
         "batched": {"filters_per_gpu_in_flight": B, "value": world * B * len(batched_s) / bsum, "unit": "updates/s",
-                    "path": "marginalizeLaunch() on all filters, then marginalizeCollect() (one stream per filter), host wall clock incl. copies"},
+                    "path": "marginalizeLaunch() on all filters, then marginalizeCollect() (one stream per filter), host wall clock incl. copies",
+                    "value_32_in_flight": world * B2 * len(batched2_s) / b2sum},
         "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line))

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,7 +54,9 @@ struct EngineBase {
   virtual int launch_timed(float* ms) = 0;
   virtual int kernel_times(float* ms, const char** names, int cap) = 0;
   virtual int tail_profile(unsigned long long* out, int cap) = 0;
+  virtual void use_graph_reset() = 0;
   bool profile = false;
+  bool use_graph = true;
   int dtype = 0, device = 0, Mmax = 0, Tmax = 0, Omax = 0;
   int M = 0;
   double rank_thr = 1e-11;
@@ -87,6 +90,14 @@ struct Engine : EngineBase {
   int st_N = 0, st_O = 0, st_Lmax = 0, st_mode = -1;
   bool staged = false;
   bool timed_region = false;
+  // CUDA-graph replay of the update's kernel sequence when the batch signature repeats (launch-bound inner loop)
+  cudaGraphExec_t g_exec = nullptr;
+  unsigned long long g_key = ~0ull, last_key = ~0ull;
+  int g_nodes = 0;
+  void drop_graph() {
+    if (g_exec) { cudaGraphExecDestroy(g_exec); g_exec = nullptr; }
+    g_key = ~0ull; last_key = ~0ull;
+  }
   // optional per-kernel CUDA-event profile of the last launch (option key 1)
   static constexpr int kMaxEv = 24;
   cudaEvent_t ev[kMaxEv] = {};
@@ -172,6 +183,7 @@ struct Engine : EngineBase {
   ~Engine() override {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+    if (g_exec) cudaGraphExecDestroy(g_exec);
     void* dv[] = {d_st, d_P, d_P2, d_poses, d_poses2, d_off, d_idx, d_cm, d_tri, d_valid, d_src, d_accept, d_rows, d_rowoff,
                   d_scratch, d_keep, d_m, d_keepclones, d_cmeff, d_csnap, d_prof, d_obs, d_pfg, d_pfg_given, d_gamma, d_Xg, d_rg, d_Vg, d_taug, d_Z, d_Yq,
                   d_ur, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_T2, d_R2, d_TP, d_S2, d_W, d_G, d_r2, d_y, d_dx, d_idiag};
@@ -209,6 +221,7 @@ struct Engine : EngineBase {
     M = 0;
     initialized = true;
     pending_mode = -1;
+    drop_graph();
     return 0;
   }
 
@@ -287,6 +300,22 @@ struct Engine : EngineBase {
     pending_mode = mode;
     n_ev = 0;
     if (N == 0) return 0;
+    const unsigned long long key = ((unsigned long long)mode << 60) ^ ((unsigned long long)N << 40) ^ ((unsigned long long)st_O << 16) ^
+                                   ((unsigned long long)Lmax << 8) ^ (unsigned long long)M;
+    bool capturing = false;
+    const long long launches_before = launches;
+    if (use_graph && !profile) {
+      if (g_exec && key == g_key) {
+        CK(cudaGraphLaunch(g_exec, stream));
+        launches += g_nodes;
+        return queue_report(N, mode);
+      }
+      if (key == last_key) {  // second time in a row with this signature: capture it
+        CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        capturing = true;
+      }
+      last_key = key;
+    }
     mark("begin");
     const int n = 15 + 6 * M, c = 6 * M;
     mb::FeatArgs<S> a;
@@ -375,7 +404,21 @@ struct Engine : EngineBase {
         mark("k_inject");
       }
     }
+    if (capturing) {
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamEndCapture(stream, &graph));
+      if (g_exec) { cudaGraphExecDestroy(g_exec); g_exec = nullptr; }
+      CK(cudaGraphInstantiate(&g_exec, graph, 0));
+      CK(cudaGraphDestroy(graph));
+      g_key = key;
+      g_nodes = (int)(launches - launches_before);
+      CK(cudaGraphLaunch(g_exec, stream));
+    }
     CK(cudaGetLastError());
+    return queue_report(N, mode);
+  }
+
+  int queue_report(int N, int mode) {
     if (timed_region) CK(cudaEventRecord(ev_t1, stream));
     // report back (pinned), still asynchronous
     if (mode != MSCKF_B200_RESIDUALIZE) {
@@ -430,6 +473,7 @@ struct Engine : EngineBase {
     CK(cudaStreamSynchronize(stream));  // keep[] is caller memory
     std::swap(d_P, d_P2);
     std::swap(d_poses, d_poses2);
+    drop_graph();  // captured kernel arguments hold the old buffers
     M = n_keep;
     return 0;
   }
@@ -497,11 +541,13 @@ struct Engine : EngineBase {
     CK(cudaMemcpyAsync(d_P, src->d_P, sizeof(S) * (size_t)ldp * nmax, cudaMemcpyDeviceToDevice, stream));
     CK(cudaMemcpyAsync(d_poses, src->d_poses, sizeof(S) * mb::kPoseStride * (size_t)(Mmax + 1), cudaMemcpyDeviceToDevice, stream));
     CK(cudaStreamSynchronize(stream));
+    // captured kernel arguments hold scalars of the filter (noise variances, rank threshold): keep the graph only if equal
+    if (M != src->M || rank_thr != src->rank_thr || h_st->u_var != src->h_st->u_var || h_st->v_var != src->h_st->v_var) drop_graph();
+    rank_thr = src->rank_thr;
+    pending_mode = -1;
     memcpy(h_st, src->h_st, sizeof(mb::DevState<S>));
     M = src->M;
     initialized = src->initialized;
-    rank_thr = src->rank_thr;
-    pending_mode = -1;
     return 0;
   }
 
@@ -526,6 +572,8 @@ struct Engine : EngineBase {
     CK(cudaEventElapsedTime(ms, ev_t0, ev_t1));
     return 0;
   }
+
+  void use_graph_reset() override { drop_graph(); }
 
   int tail_profile(unsigned long long* out, int cap) override {
     CK(cudaSetDevice(device));
@@ -563,6 +611,7 @@ int msckf_b200_create(const msckf_b200_config* cfg, msckf_b200_engine** out) {
   if (cfg->dtype == MSCKF_B200_F32) b = new Engine<float>();
   else if (cfg->dtype == MSCKF_B200_F64) b = new Engine<double>();
   else return fail(MSCKF_B200_ERR_ARG, "bad dtype");
+  if (getenv("MSCKF_B200_NO_GRAPH")) b->use_graph = false;  // e.g. under ncu: profile plain launches
   b->dtype = cfg->dtype; b->device = cfg->device; b->Mmax = cfg->max_clones; b->Tmax = cfg->max_tracks; b->Omax = cfg->max_obs;
   int rc = (cfg->dtype == MSCKF_B200_F32) ? static_cast<Engine<float>*>(b)->alloc() : static_cast<Engine<double>*>(b)->alloc();
   if (rc != 0) { delete b; return rc; }
@@ -599,8 +648,9 @@ int msckf_b200_launch_timed(msckf_b200_engine* e, float* ms) { return e->impl->l
 int msckf_b200_kernel_times(msckf_b200_engine* e, float* ms, const char** names, int cap) { return e->impl->kernel_times(ms, names, cap); }
 int msckf_b200_tail_profile(msckf_b200_engine* e, unsigned long long* out, int cap) { return e->impl->tail_profile(out, cap); }
 int msckf_b200_set_option(msckf_b200_engine* e, int key, double value) {
-  if (key == 0) { e->impl->rank_thr = value; return 0; }
+  if (key == 0) { e->impl->rank_thr = value; e->impl->use_graph_reset(); return 0; }
   if (key == 1) { e->impl->profile = value != 0; return 0; }
+  if (key == 2) { e->impl->use_graph = value != 0; e->impl->use_graph_reset(); return 0; }
   return fail(MSCKF_B200_ERR_ARG, "unknown option");
 }
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src) { return dst->impl->copy_from(src->impl); }

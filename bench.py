@@ -313,10 +313,15 @@ def main():
         st = [int(x) for x in list(buf)[:40] if x]
         print("tail stamps (us since start):", [round((x - st[0]) / 1e3, 1) for x in st], file=sys.stderr)
         sj = []
-        for x in list(buf)[40:]:
+        for x in list(buf)[40:64]:
             if not x:
                 break
             sj.append(int(x))
+        dd = [int(x) for x in list(buf)[64:80]]
+        if dd[0]:
+            print("tail diag-block fine stamps, A factor, pivots 20 and 21 (ns since pivot start: dot, shfl, decide, rsqrt+stores, publish):",
+                  [[dd[6 * q + u] - dd[6 * q] for u in range(1, 6)] for q in range(2)], "pivot-to-pivot:", dd[6] - dd[0],
+                  "| block 0: loaded -> workers done (us):", round((dd[13] - dd[12]) / 1e3, 2), file=sys.stderr)
         print("jac stamps (us since start):", [round((x - sj[0]) / 1e3, 1) for x in sj], file=sys.stderr)
     work.set_option(1, 0.0)
     kern_ms = {k: float(np.mean(v[1:])) for k, v in per.items()}

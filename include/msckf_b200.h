@@ -111,7 +111,9 @@ int msckf_b200_get_counters(msckf_b200_engine* e, long long* counters);
 int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap);
 /* option keys: 0 = rank threshold of the compression (relative pivot of the basis Gram matrix = squared sine to the span of the previous basis vectors, default 1e-11);
  *              1 = record per-kernel CUDA events in _launch (profiling aid, default off);
- *              2 = replay the update's kernel sequence as a CUDA graph when the batch signature repeats (default on) */
+ *              2 = replay the update's kernel sequence as a CUDA graph when the batch signature repeats (default on);
+ *              3 = fuse the forward substitution into the blocked Cholesky of the tail kernel where the window allows it
+ *                  (15 + 6M <= 255; default on; 0 = always run it as a separate sweep -- same results up to rounding) */
 int msckf_b200_set_option(msckf_b200_engine* e, int key, double value);
 /* checkpoint / resume: copy the complete filter state of src into dst (same dtype and capacities) */
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src);

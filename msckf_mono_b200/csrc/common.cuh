@@ -35,6 +35,10 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// out-of-line versions for code that runs once per CTA in a single warp (k_jac's QR section has ~40 reductions: inlined,
+// the shuffle sequences alone are 2400 instructions, and that section is bound by instruction fetch)
+__device__ __noinline__ float warp_sum_call(float v) { return warp_sum(v); }
+__device__ __noinline__ double warp_sum_call(double v) { return warp_sum(v); }
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -49,6 +53,9 @@ __device__ __forceinline__ double warp_max(double v) {
 template <class S> __device__ __forceinline__ S tsqrt(S x);
 template <> __device__ __forceinline__ float tsqrt<float>(float x) { return sqrtf(x); }
 template <> __device__ __forceinline__ double tsqrt<double>(double x) { return sqrt(x); }
+template <class S> __device__ __forceinline__ S trsqrt(S x);
+template <> __device__ __forceinline__ float trsqrt<float>(float x) { return rsqrtf(x); }
+template <> __device__ __forceinline__ double trsqrt<double>(double x) { return rsqrt(x); }
 template <class S> __device__ __forceinline__ S tabs(S x) { return x < S(0) ? -x : x; }
 
 // Eigen QuaternionBase::toRotationMatrix restated; q = (x,y,z,w); R row-major 3x3.

@@ -16,6 +16,7 @@
 #include "state_kernels.cuh"
 #include "tail_kernels.cuh"
 #include "tail_cluster.cuh"
+#include "tail_fused.cuh"
 
 namespace {
 thread_local std::string g_err;
@@ -57,6 +58,7 @@ struct EngineBase {
   virtual void use_graph_reset() = 0;
   bool profile = false;
   bool use_graph = true;
+  bool no_fused_tail = false;  // option 3 = 0: substitution as a separate sweep even where the fused form fits
   int dtype = 0, device = 0, Mmax = 0, Tmax = 0, Omax = 0;
   int M = 0;
   double rank_thr = 1e-11;
@@ -175,8 +177,9 @@ struct Engine : EngineBase {
     // opt in to large dynamic shared memory
     CK(cudaFuncSetAttribute(mb::k_tri<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_jac<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_tail<S, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_tail<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_tail_fused<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_tail<S, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_tail<S, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaStreamSynchronize(stream));
     return 0;
   }
@@ -373,7 +376,9 @@ struct Engine : EngineBase {
       // rank decision + Cholesky + substitution + covariance/state update: one cluster kernel (scratch for Gamma: d_G)
       {
         const int ldt = (n + 3) & ~3;
-        auto smem_for = [&](int NB) { return sizeof(double) * ((size_t)2 * NB * (NB + 1) + 2 + (size_t)2 * NB * ldt + ((n + 1) & ~1) + 2 * NB) + 64; };
+        auto smem_for = [&](int NB, bool) {
+          return sizeof(double) * ((size_t)2 * NB * (NB + 1) + 2 + (size_t)2 * NB * ldt + ((n + 1) & ~1) + 2 * NB) + 64;
+        };
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(kTailCluster, 1, 1);
         cfg.blockDim = dim3(mb::kTailThreads, 1, 1);
@@ -382,14 +387,23 @@ struct Engine : EngineBase {
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = kTailCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (smem_for(32) <= kSmemBudget) {
-          cfg.dynamicSmemBytes = smem_for(32);
-          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 32>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_R2 /*receives L (R'' is consumed by k_gemm_s)*/, d_keep, d_idiag, rank_thr, d_rank, (const int*)d_m,
-                                (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_P, ldp, d_st, d_poses, d_dx, profile ? d_prof : (unsigned long long*)nullptr));
-        } else if (smem_for(16) <= kSmemBudget) {
-          cfg.dynamicSmemBytes = smem_for(16);
-          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 16>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_R2 /*receives L (R'' is consumed by k_gemm_s)*/, d_keep, d_idiag, rank_thr, d_rank, (const int*)d_m,
-                                (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_P, ldp, d_st, d_poses, d_dx, profile ? d_prof : (unsigned long long*)nullptr));
+        unsigned long long* pf = profile ? d_prof : (unsigned long long*)nullptr;
+        // fused substitution: the RHS columns of one CTA must fit one block of W rows ((n + 1) / cluster <= 32)
+        const bool fused = (n + 1 + kTailCluster - 1) / kTailCluster <= 32 && mb::tail_fused_smem_bytes(n) <= kSmemBudget && !no_fused_tail;
+        if (fused) {
+          cfg.dynamicSmemBytes = mb::tail_fused_smem_bytes(n);
+          // T'' is dead after k_gemm_s: the kernel patches it into Gamma in place
+          CK(cudaLaunchKernelEx(&cfg, mb::k_tail_fused<S>, n, ld, d_T2, d_S2, rank_thr, d_rank, (const int*)d_m,
+                                (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_dx, d_G /*scratch*/, pf));
+        } else if (smem_for(32, false) <= kSmemBudget) {
+          cfg.dynamicSmemBytes = smem_for(32, false);
+          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 32, false>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_R2 /*receives L (R'' is consumed by k_gemm_s)*/,
+                                d_keep, d_idiag, rank_thr, d_rank, (const int*)d_m, (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_P, ldp, d_st,
+                                d_poses, d_dx, pf));
+        } else if (smem_for(16, false) <= kSmemBudget) {
+          cfg.dynamicSmemBytes = smem_for(16, false);
+          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 16, false>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_R2, d_keep, d_idiag, rank_thr, d_rank,
+                                (const int*)d_m, (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_P, ldp, d_st, d_poses, d_dx, pf));
         } else return fail(MSCKF_B200_ERR_CAPACITY, "k_tail shared memory");
       }
       launches++;
@@ -612,6 +626,7 @@ int msckf_b200_create(const msckf_b200_config* cfg, msckf_b200_engine** out) {
   else if (cfg->dtype == MSCKF_B200_F64) b = new Engine<double>();
   else return fail(MSCKF_B200_ERR_ARG, "bad dtype");
   if (getenv("MSCKF_B200_NO_GRAPH")) b->use_graph = false;  // e.g. under ncu: profile plain launches
+  if (getenv("MSCKF_B200_NO_FUSED_TAIL")) b->no_fused_tail = true;
   b->dtype = cfg->dtype; b->device = cfg->device; b->Mmax = cfg->max_clones; b->Tmax = cfg->max_tracks; b->Omax = cfg->max_obs;
   int rc = (cfg->dtype == MSCKF_B200_F32) ? static_cast<Engine<float>*>(b)->alloc() : static_cast<Engine<double>*>(b)->alloc();
   if (rc != 0) { delete b; return rc; }
@@ -651,6 +666,7 @@ int msckf_b200_set_option(msckf_b200_engine* e, int key, double value) {
   if (key == 0) { e->impl->rank_thr = value; e->impl->use_graph_reset(); return 0; }
   if (key == 1) { e->impl->profile = value != 0; return 0; }
   if (key == 2) { e->impl->use_graph = value != 0; e->impl->use_graph_reset(); return 0; }
+  if (key == 3) { e->impl->no_fused_tail = value == 0; e->impl->use_graph_reset(); return 0; }
   return fail(MSCKF_B200_ERR_ARG, "unknown option");
 }
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src) { return dst->impl->copy_from(src->impl); }

@@ -304,11 +304,59 @@ __device__ __forceinline__ void block_sum3(double v[3], double* red /*[3 * JT/32
   }
 }
 
+// ---- single-warp Cholesky for the gate (up to 63 rows + the right-hand side as an extra row).
+// The matrix lives in shared memory as a padded row-major array Yf[64][kCholLd] holding the STRICTLY lower triangle
+// (upper triangle and diagonal slots are zero; the diagonal sits in dg[]), the right-hand side as row rho.  Lane l owns
+// rows l and l + 32.  Left-looking: per pivot one dot product per owned row over the finished columns, read 4 columns at
+// a time (the row stride keeps the 16-byte loads conflict-free) -- rolled loops on purpose: unrolling this by hand into
+// register-resident rows makes ~100 KB of straight-line code that runs once per CTA and is bound by instruction fetch.
+constexpr int kCholRows = 64, kCholLd = 68;
+
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
+  const double2 t = *reinterpret_cast<const double2*>(p), u = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
+}
+
+template <class S>
+__device__ __forceinline__ bool chol_warp(S* Yf, const S* dg, int rho, int lane) {
+  const S d0 = (lane < rho) ? dg[lane] : S(1), d1 = (lane + 32 < rho) ? dg[lane + 32] : S(1);
+  S* row0 = Yf + lane * kCholLd;
+  S* row1 = Yf + (lane + 32) * kCholLd;
+  for (int k = 0; k < rho; ++k) {
+    const S* prow = Yf + k * kCholLd;  // pivot row: final left of the diagonal, zero from the diagonal on
+    S a0[4] = {S(0), S(0), S(0), S(0)}, a1[4] = {S(0), S(0), S(0), S(0)};
+    for (int c0 = 0; c0 < k; c0 += 8) {
+      S p0[4], p1[4], x0[4], x1[4], y0[4], y1[4];
+      ld4(prow + c0, p0); ld4(prow + c0 + 4, p1);
+      ld4(row0 + c0, x0); ld4(row0 + c0 + 4, x1);
+      ld4(row1 + c0, y0); ld4(row1 + c0 + 4, y1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a0[u] += x0[u] * p0[u]; a1[u] += y0[u] * p0[u]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a0[u] += x1[u] * p1[u]; a1[u] += y1[u] * p1[u]; }
+    }
+    const S s0 = ((lane == k) ? d0 : row0[k]) - ((a0[0] + a0[1]) + (a0[2] + a0[3]));
+    const S s1 = ((lane + 32 == k) ? d1 : row1[k]) - ((a1[0] + a1[1]) + (a1[2] + a1[3]));
+    const S piv = __shfl_sync(0xffffffffu, (k >= 32) ? s1 : s0, k & 31);
+    if (!(piv > S(0))) return false;
+    const S inv = trsqrt<S>(piv);
+    if (lane > k && lane <= rho) row0[k] = s0 * inv;
+    if (lane + 32 > k && lane + 32 <= rho) row1[k] = s1 * inv;
+    __syncwarp();
+  }
+  return true;
+}
+
 template <class S>
 __host__ __device__ inline size_t jac_smem_bytes(int L, int M) {
-  // bar 16 | poses M*8 S | U64 6L doubles | X 12L | r 2L | V 6L | wv 2L | pv 2L | Ypacked L(2L+1)  (S) | pad
+  // bar 16 | poses M*8 S | U64 6L doubles | X 12L | r 2L | V 6L | W 6L | F 6L | Ypacked L(2L+1)  (S) | pad |
+  // Yf 64 x 68 + dg 64 (S): the single-warp gate Cholesky's row-major copy
   return 16 + sizeof(S) * kPoseStride * (size_t)M + 16 + sizeof(double) * 6 * (size_t)L +
-         sizeof(S) * ((size_t)24 * L + (size_t)L * (2 * L + 1)) + 16;
+         sizeof(S) * ((size_t)32 * L + (size_t)L * (2 * L + 1)) + 32 + sizeof(S) * ((size_t)kCholRows * kCholLd + kCholRows);
 }
 
 // calcResidual + calcMeasJacobian + gatingTest for one feature per CTA (JT threads), with loop A's bookkeeping
@@ -321,7 +369,6 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   S* poses = reinterpret_cast<S*>(smem_raw + 16);
   stage_table_tma(poses, a.poses, (unsigned)(a.M * kPoseStride * sizeof(S)), bar);
   __shared__ double redd[JT / 32];
-  __shared__ double redd3[3 * (JT / 32)];
   __shared__ S reds[JT / 32];
   __shared__ int redi[JT / 32];
   __shared__ int s_he, s_valid, s_src, s_pushed_t;
@@ -414,9 +461,12 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   S* X = reinterpret_cast<S*>(U + 3 * L2);
   S* r = X + 12 * L;
   S* V = r + L2;
-  S* wv = V + 3 * L2;
-  S* pv = wv + L2;
-  S* Y = pv + L2;
+  S* wv = V + 3 * L2;   // [2L][3]  W = Y V
+  S* Fv = wv + 3 * L2;  // [2L][3]  F of the two-sided transform
+  S* Y = Fv + 3 * L2;
+  S* Yf = reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(Y + (size_t)L * (L2 + 1)) + 15) & ~uintptr_t(15));  // [64][68]
+  S* dgv = Yf + kCholRows * kCholLd;  // [64]
+  const bool warp_chol = (L2 - 3 + 1 <= kCholRows);  // the gate matrix and its right-hand side fit the single-warp form
   const int* idx = a.clone_idx + o0;
   const S* z = a.obs + 2 * (size_t)o0;
   const DevState<S>* st = a.st;
@@ -473,119 +523,146 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   }
   __syncthreads();
   stamp();  // X, r
-  // ---- column-pivoted Householder QR of H_f (2L x 3): the trailing 2L-3 columns of Q are A_j (msckf.h:954-955)
-  S tau[3];
+  // ---- warp 0: column-pivoted Householder QR of H_f (2L x 3) -- the trailing 2L-3 columns of Q are A_j
+  // (msckf.h:954-955) -- then U, U^T r, r~ and the compact-WY factor, all warp-synchronous (shuffle reductions, no CTA
+  // barriers).  Warps 1..3 meanwhile: Y = X P_sub X^T.
+  __shared__ S s_tau[3];
+  __shared__ S s_T[9];
+  __shared__ double s_urv[3];
+  const int warp = tid >> 5;
+  if (warp == 0) {
+    S tau[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    S nn[3] = {S(-1), S(-1), S(-1)};
-    for (int cc = k; cc < 3; ++cc) {
-      S sacc = 0;
-      for (int row = k + tid; row < L2; row += JT) sacc += V[3 * row + cc] * V[3 * row + cc];
-      nn[cc] = block_sum(sacc, reds);
-    }
-    int piv = k;
-    S best = nn[k];
-    for (int cc = k + 1; cc < 3; ++cc)
-      if (nn[cc] > best) { best = nn[cc]; piv = cc; }
-    if (piv != k)
-      for (int row = tid; row < L2; row += JT) { const S tmp = V[3 * row + k]; V[3 * row + k] = V[3 * row + piv]; V[3 * row + piv] = tmp; }
-    __syncthreads();
-    S tacc = 0;
-    for (int row = k + 1 + tid; row < L2; row += JT) tacc += V[3 * row + k] * V[3 * row + k];
-    const S tail = block_sum(tacc, reds);
-    const S c0 = V[3 * k + k];
-    S beta, tk;
-    __syncthreads();
-    if (tail <= S(sizeof(S) == 4 ? 1.17549435e-38 : 2.2250738585072014e-308)) {
-      beta = c0; tk = S(0);
-      for (int row = k + 1 + tid; row < L2; row += JT) V[3 * row + k] = S(0);
-    } else {
-      beta = tsqrt<S>(c0 * c0 + tail);
-      if (c0 >= S(0)) beta = -beta;
-      const S dd = c0 - beta;
-      for (int row = k + 1 + tid; row < L2; row += JT) V[3 * row + k] /= dd;
-      tk = (beta - c0) / beta;
-    }
-    tau[k] = tk;
-    __syncthreads();
-    if (tk != S(0)) {
-      for (int cc = k + 1; cc < 3; ++cc) {
+    for (int k = 0; k < 3; ++k) {
+      S nn[3] = {S(-1), S(-1), S(-1)};
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        if (cc < k) continue;
         S sacc = 0;
-        for (int row = k + 1 + tid; row < L2; row += JT) sacc += V[3 * row + k] * V[3 * row + cc];
-        S sdot = block_sum(sacc, reds) + V[3 * k + cc];
-        sdot *= tk;
-        __syncthreads();
-        for (int row = k + 1 + tid; row < L2; row += JT) V[3 * row + cc] -= V[3 * row + k] * sdot;
-        if (tid == 0) V[3 * k + cc] -= sdot;
-        __syncthreads();
+        _Pragma("unroll 1") for (int row = k + lane; row < L2; row += 32) sacc += V[3 * row + cc] * V[3 * row + cc];
+        nn[cc] = warp_sum_call(sacc);
       }
-    }
-    if (tid == 0) {
-      V[3 * k + k] = S(1);                                // unit diagonal of the Householder vector
-      for (int row = 0; row < k; ++row) V[3 * row + k] = S(0);  // zero above: V(:,k) is the full vector v_k
-    }
-    __syncthreads();
-  }
-  stamp();  // colpiv QR
-  // export v_k, tau for the explicit-row kernel
-  for (int e = tid; e < 3 * L2; e += JT) a.Vg[3 * 2 * (size_t)o0 + e] = V[e];
-  if (tid < 3) a.taug[3 * t + tid] = tau[tid];
-  // ---- exact reflectors for the Gram stage: H_k = I - tau64_k v_k v_k^T with tau64_k = 2 / (v_k^T v_k) in fp64, so that
-  // Q = H_0 H_1 H_2 is orthogonal to 1e-16 whatever the filter precision: G_j = I - U_j U_j^T is an exact projector
-  // and the body Gram terms and the explicit rows (k_rows) describe the same H_o.
-  double tau64[3];
-  {
-    double vv3[3] = {0.0, 0.0, 0.0};
-    for (int row = tid; row < L2; row += JT)  // v_k is zero above row k
+      int piv = k;
+      S best = nn[k];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { const double vv = (double)V[3 * row + k]; vv3[k] += vv * vv; }
-    block_sum3(vv3, redd3);
+      for (int cc = 1; cc < 3; ++cc)
+        if (cc > k && nn[cc] > best) { best = nn[cc]; piv = cc; }
+      if (piv != k)
+        _Pragma("unroll 1") for (int row = lane; row < L2; row += 32) { const S tmp = V[3 * row + k]; V[3 * row + k] = V[3 * row + piv]; V[3 * row + piv] = tmp; }
+      __syncwarp();
+      S tacc = 0;
+      _Pragma("unroll 1") for (int row = k + 1 + lane; row < L2; row += 32) tacc += V[3 * row + k] * V[3 * row + k];
+      const S tail = warp_sum_call(tacc);
+      const S c0 = V[3 * k + k];
+      S beta, tk;
+      __syncwarp();
+      if (tail <= S(sizeof(S) == 4 ? 1.17549435e-38 : 2.2250738585072014e-308)) {
+        beta = c0; tk = S(0);
+        _Pragma("unroll 1") for (int row = k + 1 + lane; row < L2; row += 32) V[3 * row + k] = S(0);
+      } else {
+        beta = tsqrt<S>(c0 * c0 + tail);
+        if (c0 >= S(0)) beta = -beta;
+        const S dd = c0 - beta;
+        _Pragma("unroll 1") for (int row = k + 1 + lane; row < L2; row += 32) V[3 * row + k] /= dd;
+        tk = (beta - c0) / beta;
+      }
+      tau[k] = tk;
+      __syncwarp();
+      if (tk != S(0)) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) tau64[k] = (tau[k] != S(0)) ? 2.0 / vv3[k] : 0.0;
-  }
-  // ---- U = Q(:,0:3) = H0 H1 H2 [I3; 0]  (fp64)
-  for (int e = tid; e < 3 * L2; e += JT) U[e] = ((e / 3) == (e % 3)) ? 1.0 : 0.0;
-  __syncthreads();
-#pragma unroll
-  for (int k = 2; k >= 0; --k) {
-    double sd[3] = {0.0, 0.0, 0.0};
-    for (int row = k + tid; row < L2; row += JT) {
-      const double vk = (double)V[3 * row + k];
-      sd[0] += vk * U[3 * row]; sd[1] += vk * U[3 * row + 1]; sd[2] += vk * U[3 * row + 2];
+        for (int cc = 1; cc < 3; ++cc) {
+          if (cc <= k) continue;
+          S sacc = 0;
+          _Pragma("unroll 1") for (int row = k + 1 + lane; row < L2; row += 32) sacc += V[3 * row + k] * V[3 * row + cc];
+          S sdot = warp_sum_call(sacc) + V[3 * k + cc];
+          sdot *= tk;
+          __syncwarp();
+          _Pragma("unroll 1") for (int row = k + 1 + lane; row < L2; row += 32) V[3 * row + cc] -= V[3 * row + k] * sdot;
+          if (lane == 0) V[3 * k + cc] -= sdot;
+          __syncwarp();
+        }
+      }
+      if (lane == 0) {
+        V[3 * k + k] = S(1);                                // unit diagonal of the Householder vector
+        for (int row = 0; row < k; ++row) V[3 * row + k] = S(0);  // zero above: V(:,k) is the full vector v_k
+      }
+      __syncwarp();
     }
-    block_sum3(sd, redd3);
-    sd[0] *= tau64[k]; sd[1] *= tau64[k]; sd[2] *= tau64[k];
-    for (int row = k + tid; row < L2; row += JT) {
-      const double vk = (double)V[3 * row + k];
-      U[3 * row] -= sd[0] * vk; U[3 * row + 1] -= sd[1] * vk; U[3 * row + 2] -= sd[2] * vk;
-    }
-    __syncthreads();
-  }
-  // U^T r in fp64 from the raw residual
-  double urv[3] = {0.0, 0.0, 0.0};
-  for (int row = tid; row < L2; row += JT) {
-    const double rr = (double)r[row];
-    urv[0] += U[3 * row] * rr; urv[1] += U[3 * row + 1] * rr; urv[2] += U[3 * row + 2] * rr;
-  }
-  block_sum3(urv, redd3);
-  // ---- r~ = H2 H1 H0 r in the filter precision (r_o = r~[3:], used by the gate only)
+    // export v_k, tau for the explicit-row kernel
+    _Pragma("unroll 1") for (int e = lane; e < 3 * L2; e += 32) a.Vg[3 * 2 * (size_t)o0 + e] = V[e];
+    if (lane < 3) { a.taug[3 * t + lane] = tau[lane == 0 ? 0 : (lane == 1 ? 1 : 2)]; }
+    // ---- exact reflectors for the Gram stage: H_k = I - tau64_k v_k v_k^T with tau64_k = 2 / (v_k^T v_k) in fp64, so
+    // that Q = H_0 H_1 H_2 is orthogonal to 1e-16 whatever the filter precision: G_j = I - U_j U_j^T is an exact
+    // projector and the body Gram terms and the explicit rows (k_rows) describe the same H_o.
+    double tau64[3];
+    S vtv01 = 0, vtv02 = 0, vtv12 = 0;  // v_a^T v_b for the compact-WY factor
+    {
+      double vv3[3] = {0.0, 0.0, 0.0};
+      _Pragma("unroll 1") for (int row = lane; row < L2; row += 32) {  // v_k is zero above row k
+        const S v0 = V[3 * row], v1 = V[3 * row + 1], v2 = V[3 * row + 2];
+        vv3[0] += (double)v0 * (double)v0; vv3[1] += (double)v1 * (double)v1; vv3[2] += (double)v2 * (double)v2;
+        vtv01 += v0 * v1; vtv02 += v0 * v2; vtv12 += v1 * v2;
+      }
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    S sacc = 0;
-    for (int row = k + tid; row < L2; row += JT) sacc += V[3 * row + k] * r[row];
-    const S sdot = tau[k] * block_sum(sacc, reds);
-    __syncthreads();
-    for (int row = k + tid; row < L2; row += JT) r[row] -= sdot * V[3 * row + k];
-    __syncthreads();
-  }
-  stamp();  // U, ur, r~
-  // ---- gating (msckf.h:1103-1124): gamma = r_o^T (H_o P H_o^T + u_var I)^-1 r_o with H_o = (Q^T X)[3:]
-  // Y = X P_sub X^T, symmetric 2L x 2L, packed lower
-  {
+      for (int k = 0; k < 3; ++k) { vv3[k] = warp_sum_call(vv3[k]); tau64[k] = (tau[k] != S(0)) ? 2.0 / vv3[k] : 0.0; }
+      vtv01 = warp_sum_call(vtv01); vtv02 = warp_sum_call(vtv02); vtv12 = warp_sum_call(vtv12);
+    }
+    // ---- U = Q(:,0:3) = H0 H1 H2 [I3; 0]  (fp64)
+    _Pragma("unroll 1") for (int e = lane; e < 3 * L2; e += 32) U[e] = ((e / 3) == (e % 3)) ? 1.0 : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 2; k >= 0; --k) {
+      double sd[3] = {0.0, 0.0, 0.0};
+      _Pragma("unroll 1") for (int row = k + lane; row < L2; row += 32) {
+        const double vk = (double)V[3 * row + k];
+        sd[0] += vk * U[3 * row]; sd[1] += vk * U[3 * row + 1]; sd[2] += vk * U[3 * row + 2];
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) sd[q] = warp_sum_call(sd[q]) * tau64[k];
+      _Pragma("unroll 1") for (int row = k + lane; row < L2; row += 32) {
+        const double vk = (double)V[3 * row + k];
+        U[3 * row] -= sd[0] * vk; U[3 * row + 1] -= sd[1] * vk; U[3 * row + 2] -= sd[2] * vk;
+      }
+      __syncwarp();
+    }
+    // U^T r in fp64 from the raw residual
+    {
+      double urv[3] = {0.0, 0.0, 0.0};
+      _Pragma("unroll 1") for (int row = lane; row < L2; row += 32) {
+        const double rr = (double)r[row];
+        urv[0] += U[3 * row] * rr; urv[1] += U[3 * row + 1] * rr; urv[2] += U[3 * row + 2] * rr;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) urv[q] = warp_sum_call(urv[q]);
+      if (lane == 0) { s_urv[0] = urv[0]; s_urv[1] = urv[1]; s_urv[2] = urv[2]; }
+    }
+    // ---- r~ = H2 H1 H0 r in the filter precision (r_o = r~[3:], used by the gate only)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      S sacc = 0;
+      _Pragma("unroll 1") for (int row = k + lane; row < L2; row += 32) sacc += V[3 * row + k] * r[row];
+      const S sdot = tau[k] * warp_sum_call(sacc);
+      _Pragma("unroll 1") for (int row = k + lane; row < L2; row += 32) r[row] -= sdot * V[3 * row + k];
+      __syncwarp();
+    }
+    // ---- compact WY: H0 H1 H2 = I - V T V^T, T upper triangular (forward accumulation)
+    if (lane == 0) {
+      const S t00 = tau[0], t11 = tau[1], t22 = tau[2];
+      const S t01 = -t11 * (t00 * vtv01);
+      const S t02 = -t22 * (t00 * vtv02 + t01 * vtv12);
+      const S t12 = -t22 * (t11 * vtv12);
+      s_T[0] = t00; s_T[1] = t01; s_T[2] = t02;
+      s_T[3] = S(0); s_T[4] = t11; s_T[5] = t12;
+      s_T[6] = S(0); s_T[7] = S(0); s_T[8] = t22;
+      s_tau[0] = t00; s_tau[1] = t11; s_tau[2] = t22;
+    }
+  } else {
+    // ---- gating (msckf.h:1103-1124): gamma = r_o^T (H_o P H_o^T + u_var I)^-1 r_o with H_o = (Q^T X)[3:]
+    // Y = X P_sub X^T, symmetric 2L x 2L, packed lower
     const int npairs = L * (L + 1) / 2;
     const S* P = a.P;
     const int ldp = a.ldp;
-    for (int p = tid; p < npairs; p += JT) {
+    for (int p = tid - 32; p < npairs; p += JT - 32) {
       int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
       while (i * (i + 1) / 2 > p) --i;
       while ((i + 1) * (i + 2) / 2 <= p) ++i;
@@ -619,86 +696,137 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
     }
   }
   __syncthreads();
-  stamp();  // Y pairs
-  // two-sided reflectors: Y <- H_k Y H_k on the trailing (>= k) block
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const S tk = tau[k];
-    if (tk != S(0)) {
-      for (int ar = k + tid; ar < L2; ar += JT) {
-        S w4[4] = {S(0), S(0), S(0), S(0)};
-        const S* rowa = Y + pk(ar, 0);
-        int b = k;
-        for (; b + 4 <= ar + 1; b += 4) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) w4[u] += rowa[b + u] * V[3 * (b + u) + k];
+  stamp();  // QR, U, r~ (warp 0) | Y pairs (warps 1..3)
+  const double urv[3] = {s_urv[0], s_urv[1], s_urv[2]};
+  // ---- two-sided transform in one pass: Q^T Y Q = Y - (V F^T + F V^T),  F = W T - V (T^T B T) / 2,  W = Y V,  B = V^T W
+  S* Wv = wv;  // [L2][3]  (wv and pv are contiguous: 2 * L2 each, >= 3 * L2 + ... see jac_smem_bytes)
+  {
+    // W = Y V: two threads per row (row part | column part of the packed symmetric storage)
+    for (int base = 0; base < L2; base += JT / 2) {
+      const int ar = base + (tid >> 1), h = tid & 1;
+      S w0 = 0, w1 = 0, w2 = 0;
+      if (ar < L2) {
+        if (h == 0) {
+          const S* rowa = Y + pk(ar, 0);
+          for (int b = 0; b <= ar; ++b) { const S y = rowa[b]; w0 += y * V[3 * b]; w1 += y * V[3 * b + 1]; w2 += y * V[3 * b + 2]; }
+        } else {
+          for (int b = ar + 1; b < L2; ++b) { const S y = Y[pk(b, ar)]; w0 += y * V[3 * b]; w1 += y * V[3 * b + 1]; w2 += y * V[3 * b + 2]; }
         }
-        for (; b <= ar; ++b) w4[0] += rowa[b] * V[3 * b + k];
-        for (b = ar + 1; b + 4 <= L2; b += 4) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) w4[u] += Y[pk(b + u, ar)] * V[3 * (b + u) + k];
-        }
-        for (; b < L2; ++b) w4[0] += Y[pk(b, ar)] * V[3 * b + k];
-        wv[ar] = (w4[0] + w4[1]) + (w4[2] + w4[3]);
       }
-      __syncthreads();
-      S aacc = 0;
-      for (int ar = k + tid; ar < L2; ar += JT) aacc += V[3 * ar + k] * wv[ar];
-      const S alpha = block_sum(aacc, reds);
-      const S hc = tk * tk * alpha * S(0.5);
-      for (int ar = k + tid; ar < L2; ar += JT) pv[ar] = tk * wv[ar] - hc * V[3 * ar + k];
-      __syncthreads();
-      for (int ar = k + (tid >> 5); ar < L2; ar += JT / 32) {  // one row per warp, lanes along the row
-        const S va = V[3 * ar + k], pa = pv[ar];
-        for (int b = k + lane; b <= ar; b += 32) Y[pk(ar, b)] -= va * pv[b] + pa * V[3 * b + k];
-      }
-      __syncthreads();
-    }
-  }
-  stamp();  // two-sided reflectors
-  // S = Y[3:,3:] + u_var I ; left-looking Cholesky, one matrix row per thread (threads >= rows idle), the right-hand
-  // side r~[3:] rides along as an extra row.  Per column: one dot product over the finished columns (contiguous in the
-  // packed row), the pivot broadcast through shared memory, two barriers.
-  const S uvar = st->u_var;
-  for (int j = 3 + tid; j < L2; j += JT) Y[pk(j, j)] += uvar;
-  __shared__ S s_piv;
-  bool chol_ok = true;
-  for (int j = 3; j < L2; ++j) {
-    __syncthreads();
-    // rows i = j .. L2-1 and the extra row (index L2): strided over the CTA's threads
-    S sv[2] = {S(0), S(0)};
-    int cnt = 0;
-    for (int i = j + tid; i <= L2; i += JT, ++cnt) {
-      const S* rowi = (i < L2) ? (Y + pk(i, 0)) : nullptr;
-      const S* rowj = Y + pk(j, 0);
-      S sacc = (i < L2) ? rowi[j] : r[j];
-      {
-        const S* src = (i < L2) ? rowi : r;  // the extra row is the right-hand side
-        S p4[4] = {S(0), S(0), S(0), S(0)};  // 4 partial sums: short FMA chains, loads issued back to back
-        int cc = 3;
-        for (; cc + 4 <= j; cc += 4) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) p4[u] += src[cc + u] * rowj[cc + u];
-        }
-        for (; cc < j; ++cc) p4[0] += src[cc] * rowj[cc];
-        sacc -= (p4[0] + p4[1]) + (p4[2] + p4[3]);
-      }
-      if (cnt < 2) sv[cnt] = sacc;
-      if (i == j) s_piv = sacc;
-    }
-    __syncthreads();
-    const S dj = s_piv;
-    if (!(dj > S(0))) { chol_ok = false; break; }
-    const S inv = S(1) / tsqrt<S>(dj);
-    cnt = 0;
-    for (int i = j + tid; i <= L2; i += JT, ++cnt) {
-      const S v = sv[cnt < 2 ? cnt : 1] * inv;
-      if (i < L2) Y[pk(i, j)] = v; else r[j] = v;
+      w0 += __shfl_xor_sync(0xffffffffu, w0, 1); w1 += __shfl_xor_sync(0xffffffffu, w1, 1); w2 += __shfl_xor_sync(0xffffffffu, w2, 1);
+      if (ar < L2 && h == 0) { Wv[3 * ar] = w0; Wv[3 * ar + 1] = w1; Wv[3 * ar + 2] = w2; }
     }
   }
   __syncthreads();
+  if (warp == 0) {
+    S Bm[6] = {0, 0, 0, 0, 0, 0};  // B = V^T W (symmetric): 00 01 02 11 12 22
+    for (int row = lane; row < L2; row += 32) {
+      const S v0 = V[3 * row], v1 = V[3 * row + 1], v2 = V[3 * row + 2];
+      const S w0 = Wv[3 * row], w1 = Wv[3 * row + 1], w2 = Wv[3 * row + 2];
+      Bm[0] += v0 * w0; Bm[1] += v0 * w1; Bm[2] += v0 * w2; Bm[3] += v1 * w1; Bm[4] += v1 * w2; Bm[5] += v2 * w2;
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) Bm[q] = warp_sum_call(Bm[q]);
+    const S Bf[3][3] = {{Bm[0], Bm[1], Bm[2]}, {Bm[1], Bm[3], Bm[4]}, {Bm[2], Bm[4], Bm[5]}};
+    S Tm[3][3], BT[3][3], G3[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Tm[i][j] = s_T[3 * i + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) BT[i][j] = Bf[i][0] * Tm[0][j] + Bf[i][1] * Tm[1][j] + Bf[i][2] * Tm[2][j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) G3[i][j] = S(0.5) * (Tm[0][i] * BT[0][j] + Tm[1][i] * BT[1][j] + Tm[2][i] * BT[2][j]);
+    __syncwarp();
+    for (int row = lane; row < L2; row += 32) {
+      const S v0 = V[3 * row], v1 = V[3 * row + 1], v2 = V[3 * row + 2];
+      const S w0 = Wv[3 * row], w1 = Wv[3 * row + 1], w2 = Wv[3 * row + 2];
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Fv[3 * row + j] = (w0 * Tm[0][j] + w1 * Tm[1][j] + w2 * Tm[2][j]) - (v0 * G3[0][j] + v1 * G3[1][j] + v2 * G3[2][j]);
+    }
+  }
+  __syncthreads();
+  // only the trailing block [3:, 3:] is used below.  Single-warp gate: the transformed block goes straight into the padded
+  // row-major copy (strictly lower part; diagonal + u_var into dgv; right-hand side as row rho).
+  const S uvar = st->u_var;
+  const int rho = L2 - 3;
+  if (warp_chol) {
+    for (int e = tid; e < kCholRows * kCholLd; e += JT) {
+      const int q = e / kCholLd, cc = e % kCholLd;
+      Yf[e] = (q == rho && cc < rho) ? r[3 + cc] : S(0);
+    }
+    __syncthreads();
+  }
+  for (int ar = 3 + warp; ar < L2; ar += JT / 32) {  // one row per warp, lanes along the row
+    const S va0 = V[3 * ar], va1 = V[3 * ar + 1], va2 = V[3 * ar + 2];
+    const S fa0 = Fv[3 * ar], fa1 = Fv[3 * ar + 1], fa2 = Fv[3 * ar + 2];
+    for (int b = 3 + lane; b <= ar; b += 32) {
+      const S val = Y[pk(ar, b)] - ((va0 * Fv[3 * b] + va1 * Fv[3 * b + 1] + va2 * Fv[3 * b + 2]) + (fa0 * V[3 * b] + fa1 * V[3 * b + 1] + fa2 * V[3 * b + 2]));
+      if (!warp_chol) Y[pk(ar, b)] = val;
+      else if (b < ar) Yf[(ar - 3) * kCholLd + (b - 3)] = val;
+      else dgv[ar - 3] = val + uvar;
+    }
+  }
+  __syncthreads();
+  stamp();  // two-sided transform
+  // S = Y[3:,3:] + u_var I ; Cholesky with the right-hand side r~[3:] riding along as an extra row
+  bool chol_ok = true;
   S gacc = 0;
-  for (int j = 3 + tid; j < L2; j += JT) gacc += r[j] * r[j];
+  if (warp_chol) {
+    __shared__ int s_ok;
+    if (warp == 0) {
+      const bool ok = chol_warp<S>(Yf, dgv, rho, lane);
+      if (lane == 0) s_ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    chol_ok = s_ok != 0;
+    for (int j = tid; j < rho; j += JT) { const S v = Yf[rho * kCholLd + j]; gacc += v * v; }
+  } else {
+    // left-looking, one matrix row per thread (threads >= rows idle).  Per column: one dot product over the finished
+    // columns (contiguous in the packed row), the pivot broadcast through shared memory, two barriers.
+    for (int j = 3 + tid; j < L2; j += JT) Y[pk(j, j)] += uvar;
+    __shared__ S s_piv;
+    for (int j = 3; j < L2; ++j) {
+      __syncthreads();
+      // rows i = j .. L2-1 and the extra row (index L2): strided over the CTA's threads
+      S sv[2] = {S(0), S(0)};
+      int cnt = 0;
+      for (int i = j + tid; i <= L2; i += JT, ++cnt) {
+        const S* rowi = (i < L2) ? (Y + pk(i, 0)) : nullptr;
+        const S* rowj = Y + pk(j, 0);
+        S sacc = (i < L2) ? rowi[j] : r[j];
+        {
+          const S* src = (i < L2) ? rowi : r;  // the extra row is the right-hand side
+          S p4[4] = {S(0), S(0), S(0), S(0)};  // 4 partial sums: short FMA chains, loads issued back to back
+          int cc = 3;
+          for (; cc + 4 <= j; cc += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p4[u] += src[cc + u] * rowj[cc + u];
+          }
+          for (; cc < j; ++cc) p4[0] += src[cc] * rowj[cc];
+          sacc -= (p4[0] + p4[1]) + (p4[2] + p4[3]);
+        }
+        if (cnt < 2) sv[cnt] = sacc;
+        if (i == j) s_piv = sacc;
+      }
+      __syncthreads();
+      const S dj = s_piv;
+      if (!(dj > S(0))) { chol_ok = false; break; }
+      const S inv = S(1) / tsqrt<S>(dj);
+      cnt = 0;
+      for (int i = j + tid; i <= L2; i += JT, ++cnt) {
+        const S v = sv[cnt < 2 ? cnt : 1] * inv;
+        if (i < L2) Y[pk(i, j)] = v; else r[j] = v;
+      }
+    }
+    __syncthreads();
+    for (int j = 3 + tid; j < L2; j += JT) gacc += r[j] * r[j];
+  }
   S gam = block_sum(gacc, reds);
   const int acc = chol_ok && (gam < st->chi2[L]);  // table[dof+1], dof = L-1 (msckf.h:433,:1117)
   if (!chol_ok) gam = S(1e30);

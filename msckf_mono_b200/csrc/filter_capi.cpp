@@ -228,7 +228,10 @@ int msckf_mono_get_counters(void* h, long* out) {
 }
 int msckf_mono_set_option(void* h, int key, double v) {
   return guard([&] {
-    if (key == 100) { int rc = msckf_b200_set_option(H->engine(), 0, v); if (rc) throw std::runtime_error(msckf_b200_last_error()); }
+    if (key >= 100) {  // engine options: 100 + key of msckf_b200_set_option
+      int rc = msckf_b200_set_option(H->engine(), key - 100, v);
+      if (rc) throw std::runtime_error(msckf_b200_last_error());
+    }
     return 0;  // oracle-only keys (0..2) are accepted and ignored
   });
 }

@@ -1,0 +1,410 @@
+// msckf_mono_b200/csrc/tail_fused.cuh
+// The serial part of the EKF tail for windows up to ~35 clones as ONE thread-block-cluster kernel (8 CTAs, 8 SMs of a GPC):
+//     Gamma (Gram matrix of the basis)  -> rank decision      }  rank-revealing Cholesky of Gamma (G) and S'' (A),
+//     S'' = L L^T over the kept indices                        }  blocked by 32, A following G's decisions
+//     W = L^-1 [T''P | r'']   fused into the factorisation: every CTA keeps its share of the right-hand-side columns as
+//                             rows in shared memory and treats them as extra panel rows
+// followed by  P <- P - W^T W (k_syrk, all SMs) and dx = W^T y + state injection (k_inject)   (msckf.h:1373-1418).
+//
+// What bounds this kernel is latency, not the FP64 pipe (64 lane-FMA/clk/SM measured, scripts/fp64_rate.cu): a chain of
+// ~n dependent pivots, each a short dot product issued by ONE warp at ~8 cycles per dependent instruction.  Measured
+// (ncu source view, profiles/) and acted upon:
+//   * instruction count per pivot is what the diagonal block costs: the two factorisations run in two warps (A polls
+//     G's decision for the pivot through shared memory), two more warps build the inverses of the two factors one
+//     pivot behind, rsqrt is a float seed + two Newton steps, the dot products read 8 columns per step with 16-byte loads;
+//   * instruction fetch: hand-unrolled register-resident forms (~50-100 KB of straight-line code that runs once per
+//     block) are bound by instruction-cache misses at ~15 cycles per instruction -- every hot loop here is ROLLED;
+//   * work on the critical path: the panel below a diagonal block is X = A_panel L_kk^-T.  With L_kk^-1 at hand the
+//     panel is a small GEMM shared by all 8 warps instead of a 32-step substitution per row; panel rows are dealt to
+//     the 8 CTAs (no redundant solves) and exchanged through L2 (a scratch panel every CTA reads back after the cluster
+//     barrier: ~64 B/clk per SM, against ~20 B/clk for pushing it into 8 shared memories through DSMEM);
+//   * shared-memory bank conflicts: tiles are dealt so that the lanes of a warp read neighbouring columns.
+// Three cluster barriers (release/acquire at cluster scope) per block order the phases.
+#pragma once
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "tail_cluster.cuh"
+
+namespace mb {
+
+constexpr int kFB = 32;        // block size of the fused form
+constexpr int kFLD = kFB + 2;  // row stride of the 32 x 32 shared blocks: even (16-byte loads), conflict-free per quarter warp
+
+__host__ __device__ inline size_t tail_fused_smem_bytes(int n) {
+  const size_t ldt = (size_t)((n + 3) & ~3);
+  // DG, DA, LIG, LIA, WB [32][34] | PT_A, PT_G, Ws [32][ldt] | XT [32][32] | d0 [n] | idg, ida [32]
+  return sizeof(double) * (5 * (size_t)kFB * kFLD + 3 * (size_t)kFB * ldt + (size_t)kFB * kFB + ((n + 1) & ~1) + 2 * kFB) + 64;
+}
+
+__device__ __forceinline__ void tf_ld8(const double* p, double (&v)[8]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const double2 t = *reinterpret_cast<const double2*>(p + 2 * u);
+    v[2 * u] = t.x; v[2 * u + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void tf_ld4(const double* p, double (&v)[4]) {
+  const double2 t = *reinterpret_cast<const double2*>(p), u = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
+}
+
+// 1 / sqrt(p): float seed + two Newton steps (a dozen instructions instead of the library's ~35)
+__device__ __forceinline__ double tf_rsqrt(double p) {
+  if (p > 1e-30 && p < 1e30) {
+    double y = (double)rsqrtf((float)p);
+    const double hp = 0.5 * p;
+    y = y * (1.5 - hp * y * y);
+    y = y * (1.5 - hp * y * y);
+    return y;
+  }
+  return rsqrt(p);
+}
+
+// diagonal block -> shared [32][34]: strictly lower triangle only (zeros elsewhere); the diagonal goes to dg[]
+__device__ __forceinline__ void tf_load_diag(double* D, double* dg, const double* A, int ld, int kb, int nb, int tid) {
+  for (int e = tid; e < kFB * kFLD; e += kTailThreads) {
+    const int i = e / kFLD, j = e % kFLD;
+    double v = 0.0;
+    if (i < nb && j < i) v = A[(size_t)(kb + i) * ld + kb + j];
+    D[e] = v;
+  }
+  if (tid < kFB) dg[tid] = (tid < nb) ? A[(size_t)(kb + tid) * ld + kb + tid] : 1.0;
+}
+
+// One warp factorises a 32 x 32 block in place (lane = row, left-looking, strictly lower storage): column k of the factor
+// from the finished columns, 8 columns of the dot product per step.  decide(k, pivot) -> drop; inv[k] = 1 / L_kk (0 for a
+// dropped index, whose row and column leave the factor).  After pivot k, *step = k + 1 (followers poll it).
+#define TF_DSTAMP(i)                                                                   \
+  if (dprof && lane == 0 && k >= 20 && k < 22) {                                       \
+    unsigned long long t_;                                                             \
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory");                 \
+    dprof[6 * (k - 20) + (i)] = t_;                                                    \
+  }
+template <class Decide>
+__device__ __forceinline__ void tf_factor(double* D, double dself, double* inv, int nb, int lane, int* step, Decide decide,
+                                          unsigned long long* dprof = nullptr) {
+  constexpr int LD = kFLD;
+  double* row = D + lane * LD;
+  for (int k = 0; k < nb; ++k) {
+    TF_DSTAMP(0)
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* prow = D + k * LD;  // the pivot row is zero from its diagonal on: no masking needed
+    for (int j0 = 0; j0 < k; j0 += 8) {
+      double p[8], x[8];
+      tf_ld8(prow + j0, p);
+      tf_ld8(row + j0, x);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a4[u & 3] += x[u] * p[u];
+    }
+    TF_DSTAMP(1)
+    const double sv = ((lane == k) ? dself : row[k]) - ((a4[0] + a4[1]) + (a4[2] + a4[3]));
+    const double pv = __shfl_sync(0xffffffffu, sv, k);
+    TF_DSTAMP(2)
+    const bool drop = decide(k, pv);
+    TF_DSTAMP(3)
+    const double iv = drop ? 0.0 : tf_rsqrt(pv);
+    if (lane > k && lane < nb) row[k] = sv * iv;
+    if (drop && lane < k) D[k * LD + lane] = 0.0;
+    if (lane == k) inv[k] = iv;
+    TF_DSTAMP(4)
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(step) = k + 1; }
+    TF_DSTAMP(5)
+  }
+}
+
+// One warp builds the inverse of the block's factor one pivot behind the factorising warp (lane = column c):
+// Linv[k][c] = (delta_kc - sum_{j<k} L[k][j] Linv[j][c]) / L[k][k]; a dropped pivot (1 / L_kk := 0) gives a zero row
+__device__ __forceinline__ void tf_invert(const double* Lf, const double* inv, double* LI, int nb, int lane, const int* step) {
+  constexpr int LD = kFLD;
+  for (int k = 0; k < nb; ++k) {
+    while (*reinterpret_cast<const volatile int*>(step) <= k) { }
+    __threadfence_block();
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j0 = 0; j0 < k; j0 += 8) {  // L's row k is zero from the diagonal on
+      double p[8];
+      tf_ld8(Lf + k * LD + j0, p);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a4[u & 3] += p[u] * LI[(j0 + u) * LD + lane];
+    }
+    const double acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    const double ik = *reinterpret_cast<const volatile double*>(inv + k);
+    LI[k * LD + lane] = (lane <= k) ? ik * ((lane == k ? 1.0 : 0.0) - acc) : 0.0;
+  }
+}
+
+template <class S>
+__global__ void __launch_bounds__(kTailThreads) k_tail_fused(int n, int ld, double* __restrict__ G /*T'' on entry: patched into Gamma in place*/,
+                                                            double* __restrict__ A, double thr, int* __restrict__ rank_out,
+                                                            const int* __restrict__ m_in, const double* __restrict__ TP,
+                                                            const double* __restrict__ r2, double* __restrict__ Wm,
+                                                            double* __restrict__ yv, double* __restrict__ dx_out,
+                                                            double* __restrict__ scratch /*>= 64 * (34 + ldt) doubles*/,
+                                                            unsigned long long* __restrict__ prof /*optional phase timestamps*/) {
+  namespace cg = cooperative_groups;
+  constexpr int NB = kFB, LD = kFLD;
+  double* Lsc = scratch;                      // [2][32][34] inverses of the current diagonal blocks' factors (A, G)
+  double* Psc = scratch + 2 * NB * LD;        // [2][32][ldt] the current panels, transposed (A, G)
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int C = (int)cluster.num_blocks();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int prof_i = 0;
+  auto stamp = [&]() {
+    if (prof && blockIdx.x == 0 && tid == 0 && prof_i < 39) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) : : "memory");
+      prof[prof_i++] = t;
+    }
+  };
+  stamp();
+  extern __shared__ __align__(16) double sm[];
+  const int ldt = (n + 3) & ~3;              // row stride of the transposed panels (16-byte aligned rows)
+  double* DG = sm;                           // [32][34] diagonal block of G (CTA 0); then this CTA's panel rows of G; then X_G^T
+  double* DA = DG + NB * LD;                 // [32][34] same for A
+  double* LIG = DA + NB * LD;                // [32][34] inverse of the factor of G's block
+  double* LIA = LIG + NB * LD;               // [32][34] same for A
+  double* WB = LIA + NB * LD;                // [32][34] the current block of this CTA's W rows
+  double* PT_A = WB + NB * LD;               // [32][ldt] panel of A, transposed
+  double* PT_G = PT_A + (size_t)NB * ldt;    // [32][ldt] panel of G, transposed
+  double* Ws = PT_G + (size_t)NB * ldt;      // [32][ldt] row c = RHS column col0 + c of the substitution
+  double* XT = Ws + (size_t)NB * ldt;        // [32][32]  solved block of the W rows, transposed
+  double* d0 = XT + NB * NB;                 // [n] original diagonal of Gamma (CTA 0)
+  double* idg = d0 + ((n + 1) & ~1);         // [32] 1 / diag of the block's factor of G (0 = dropped)
+  double* ida = idg + NB;                    // [32] same for A
+  __shared__ double dgG[NB], dgA[NB];        // diagonals of the current blocks
+  __shared__ int s_rankA, s_rankG, s_stepA, s_stepG;
+  const int m = *m_in;
+  const bool full = m <= n;  // all rows explicit and orthonormal: Gamma = I_m, nothing to decide, G untouched
+  const int rank_cap = min(m, n);
+  const int gtid = crank * kTailThreads + tid, gthreads = C * kTailThreads;
+
+  if (m == 0) {  // nothing accepted: the reference returns before touching the state (msckf.h:401-403, :1328)
+    for (int a = gtid; a < n; a += gthreads) dx_out[a] = 0.0;
+    if (gtid == 0) *rank_out = 0;
+    return;
+  }
+  const int ncol = n + 1;
+  const int per = (ncol + C - 1) / C;  // RHS columns per CTA (<= 32)
+  const int col0 = crank * per, cw = max(0, min(per, ncol - col0));
+  const int ncw4 = (cw + 3) / 4;
+  // ---------------------------------------------------------------- Gamma = [[I_h, H_h], [H_h^T, Lambda]]: T'' already
+  // holds H_h (rows < 15) and Lambda; only the lower triangle is read below, so patching the first 15 columns suffices
+  if (!full) {
+    for (int e = gtid; e < n * kImuDim; e += gthreads) {
+      const int a = e / kImuDim, b = e % kImuDim;
+      G[(size_t)a * ld + b] = (a < kImuDim) ? ((a == b) ? 1.0 : 0.0) : G[(size_t)b * ld + a];
+    }
+  }
+  for (int e = tid; e < NB * n; e += kTailThreads) {  // consecutive threads -> consecutive k: conflict-free stores
+    const int c = e / n, k = e % n, col = col0 + c;
+    double v = 0.0;
+    if (c < cw) v = (col < n) ? TP[(size_t)k * ld + col] : r2[k];
+    Ws[(size_t)c * ldt + k] = v;
+  }
+  for (int e = tid; e < NB * (ldt - n); e += kTailThreads) Ws[(size_t)(e / (ldt - n)) * ldt + n + e % (ldt - n)] = 0.0;
+  cluster.sync();
+  stamp();  // Gamma patched, right-hand sides staged
+  if (crank == 0) {
+    for (int k = tid; k < n; k += kTailThreads) d0[k] = full ? (k < m ? 1.0 : 0.0) : G[(size_t)k * ld + k];
+    if (tid == 0) { s_rankA = 0; s_rankG = 0; }
+  }
+  __syncthreads();
+  // ---------------------------------------------------------------- blocked rank-revealing Cholesky (G decides, A follows)
+  for (int kb = 0; kb < n; kb += NB) {
+    const int nb = min(NB, n - kb);
+    const int r0 = kb + nb;
+    const int nr = n - r0;
+    // phase 1 (CTA 0): the diagonal blocks, four warps on four sub-partitions: G's factor (decides), A's factor (follows
+    // G's decision pivot by pivot), and the inverses of the two factors one pivot behind.
+    if (crank == 0) {
+      if (!full) tf_load_diag(DG, dgG, G, ld, kb, nb, tid);
+      tf_load_diag(DA, dgA, A, ld, kb, nb, tid);
+      for (int e = tid; e < NB * LD; e += kTailThreads) { LIA[e] = 0.0; LIG[e] = 0.0; }
+      if (tid == 0) { s_stepA = 0; s_stepG = 0; }
+      __syncthreads();
+      if (prof && kb == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[76] = t_; }
+      if (warp == 3 && !full) {
+        int rk = s_rankG;
+        tf_factor(DG, dgG[lane], idg, nb, lane, &s_stepG, [&](int k, double pv) {
+          const double dk0 = d0[kb + k];
+          const bool drop = !(dk0 > 0.0) || !(pv > thr * dk0) || rk >= rank_cap;
+          if (!drop) rk++;
+          return drop;
+        });
+        if (lane == 0) s_rankG = rk;
+      } else if (warp == 0) {
+        int rk = s_rankA;
+        tf_factor(DA, dgA[lane], ida, nb, lane, &s_stepA, [&](int k, double pv) {
+          bool drop;
+          if (full) drop = !(d0[kb + k] > 0.0) || rk >= rank_cap;
+          else {
+            while (*reinterpret_cast<volatile int*>(&s_stepG) <= k) { }
+            __threadfence_block();
+            drop = *reinterpret_cast<volatile double*>(idg + k) == 0.0;
+          }
+          drop = drop || !(pv > 0.0);
+          if (!drop) rk++;
+          return drop;
+        }, (prof && kb == 0) ? prof + 64 : nullptr);
+        if (lane == 0) s_rankA = rk;
+        for (int k = nb + lane; k < NB; k += 32) { ida[k] = 0.0; idg[k] = 0.0; }
+      } else if (warp == 1) {
+        tf_invert(DA, ida, LIA, nb, lane, &s_stepA);
+      } else if (warp == 2 && !full) {
+        tf_invert(DG, idg, LIG, nb, lane, &s_stepG);
+      }
+      __syncthreads();
+      if (prof && kb == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[77] = t_; }
+      // the inverses go to the other CTAs through L2 (a DSMEM push of 2 x 8.7 KB to 7 CTAs runs at ~20 B/clk: 3 us)
+      for (int e = tid; e < NB * LD / 2; e += kTailThreads) {
+        reinterpret_cast<double2*>(Lsc)[e] = reinterpret_cast<const double2*>(LIA)[e];
+        if (!full) reinterpret_cast<double2*>(Lsc + NB * LD)[e] = reinterpret_cast<const double2*>(LIG)[e];
+      }
+    }
+    stamp();  // diagonal block done
+    cluster.sync();
+    // phase 2: the panel below the block, X = rows * Linv^T.  Rows are dealt to the CTAs in contiguous chunks (an even
+    // number of rows each); lane = local row, warp w computes columns w, w + 8, w + 16, w + 24; the results go to a scratch
+    // panel in L2 that every CTA reads back after the barrier.  The W rows of this CTA are solved the same way (local).
+    const int chunk = (((nr + C - 1) / C) + 1) & ~1;
+    const int i0 = crank * chunk;
+    const int nloc = max(0, min(chunk, nr - i0));
+    {
+      if (crank != 0) {
+        for (int e = tid; e < NB * LD / 2; e += kTailThreads) {
+          reinterpret_cast<double2*>(LIA)[e] = __ldcg(reinterpret_cast<const double2*>(Lsc) + e);
+          if (!full) reinterpret_cast<double2*>(LIG)[e] = __ldcg(reinterpret_cast<const double2*>(Lsc + NB * LD) + e);
+        }
+      }
+      for (int e = tid; e < NB * NB; e += kTailThreads) {
+        const int l = e / NB, c = e % NB;
+        const bool in = (l < nloc && c < nb);
+        DA[l * LD + c] = in ? A[(size_t)(r0 + i0 + l) * ld + kb + c] : 0.0;
+        if (!full) DG[l * LD + c] = in ? G[(size_t)(r0 + i0 + l) * ld + kb + c] : 0.0;
+        WB[l * LD + c] = (c < nb) ? Ws[(size_t)l * ldt + kb + c] : 0.0;
+      }
+      __syncthreads();
+      double xa[4] = {0.0, 0.0, 0.0, 0.0}, xg[4] = {0.0, 0.0, 0.0, 0.0}, xw[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+      for (int c0 = 0; c0 < NB; c0 += 4) {
+        double a[4], g[4], w[4];
+        tf_ld4(DA + lane * LD + c0, a);
+        tf_ld4(WB + lane * LD + c0, w);
+        if (!full) tf_ld4(DG + lane * LD + c0, g);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = warp + 8 * jj;
+          double l[4];
+          tf_ld4(LIA + j * LD + c0, l);
+          xa[jj] += (a[0] * l[0] + a[1] * l[1]) + (a[2] * l[2] + a[3] * l[3]);
+          xw[jj] += (w[0] * l[0] + w[1] * l[1]) + (w[2] * l[2] + w[3] * l[3]);
+          if (!full) {
+            double h[4];
+            tf_ld4(LIG + j * LD + c0, h);
+            xg[jj] += (g[0] * h[0] + g[1] * h[1]) + (g[2] * h[2] + g[3] * h[3]);
+          }
+        }
+      }
+      __syncthreads();  // every warp is done reading the staged rows: DA / DG now take X^T ([j][l]) for the push
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = warp + 8 * jj;
+        DA[j * LD + lane] = xa[jj];
+        if (!full) DG[j * LD + lane] = xg[jj];
+        if (j < nb) Ws[(size_t)lane * ldt + kb + j] = xw[jj];  // final
+        XT[j * NB + lane] = (j < nb) ? xw[jj] : 0.0;
+      }
+      __syncthreads();
+      // this CTA's rows of the solved panel -> global scratch (transposed); every CTA reads the whole panel after the barrier
+      for (int e = tid; e < NB * nloc; e += kTailThreads) {
+        const int j = e / nloc, l = e % nloc;
+        Psc[(size_t)j * ldt + i0 + l] = DA[j * LD + l];
+        if (!full) Psc[(size_t)(NB + j) * ldt + i0 + l] = DG[j * LD + l];
+      }
+    }
+    stamp();  // panel computed
+    if (nr <= 0) break;  // last block: the W rows are complete
+    cluster.sync();
+    {
+      const int nr2 = (nr + 1) >> 1;  // 16-byte loads; an odd last column picks up the (finite) neighbour, zeroed below
+      for (int e = tid; e < NB * nr2; e += kTailThreads) {
+        const int j = e / nr2, l2 = 2 * (e % nr2);
+        *reinterpret_cast<double2*>(PT_A + (size_t)j * ldt + l2) = __ldcg(reinterpret_cast<const double2*>(Psc + (size_t)j * ldt + l2));
+        if (!full) *reinterpret_cast<double2*>(PT_G + (size_t)j * ldt + l2) = __ldcg(reinterpret_cast<const double2*>(Psc + (size_t)(NB + j) * ldt + l2));
+      }
+      __syncthreads();
+      const int nrp = (nr + 3) & ~3;  // zero the tail of the padded rows so that partial tiles read zeros
+      for (int e = tid; e < (nrp - nr) * NB; e += kTailThreads) {
+        const size_t o = (size_t)(e / (nrp - nr)) * ldt + nr + e % (nrp - nr);
+        PT_A[o] = 0.0;
+        if (!full) PT_G[o] = 0.0;
+      }
+      __syncthreads();
+    }
+    stamp();  // panel exchanged
+    // phase 3: trailing update, 4x4 register tiles on the transposed panels.  Work items: the lower-triangle tiles of A,
+    // then of G, dealt to the CTAs in contiguous runs (neighbouring lanes read neighbouring columns: no bank
+    // conflicts); then this CTA's own W tiles.
+    {
+      const int nt = (nr + 3) / 4, ntile = nt * (nt + 1) / 2;
+      const int nitems = full ? ntile : 2 * ntile;
+      const int run = (nitems + C - 1) / C;
+      const int first = crank * run;
+      const int mine = max(0, min(run, nitems - first));
+      const int nloc3 = mine + ncw4 * nt;
+      for (int q = tid; q < nloc3; q += kTailThreads) {
+        if (q < mine) {
+          const int it = first + q;
+          const bool isG = it >= ntile;
+          int ti, tj;
+          tc_tile_index(isG ? it - ntile : it, ti, tj);
+          double* Mat = (isG ? G : A) + (size_t)r0 * ld + r0;
+          const double* PT = isG ? PT_G : PT_A;
+          double old[4][4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {  // issue the loads of the old values before the FMA chain
+              const int i = 4 * ti + p, i2 = 4 * tj + qq;
+              old[p][qq] = (i < nr && i2 <= i) ? Mat[(size_t)i * ld + i2] : 0.0;
+            }
+          double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+          tc_tile_4x4(PT, PT, ldt, ldt, 4 * ti, 4 * tj, NB, acc);
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const int i = 4 * ti + p, i2 = 4 * tj + qq;
+              if (i < nr && i2 <= i) Mat[(size_t)i * ld + i2] = old[p][qq] - acc[p][qq];
+            }
+        } else {
+          const int w = q - mine, ti = w % nt, c4 = w / nt;
+          double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+          tc_tile_4x4(XT, PT_A, NB, ldt, 4 * c4, 4 * ti, NB, acc);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            double2* dst = reinterpret_cast<double2*>(Ws + (size_t)(4 * c4 + p) * ldt + r0 + 4 * ti);
+            double2 v0 = dst[0], v1 = dst[1];
+            v0.x -= acc[p][0]; v0.y -= acc[p][1]; v1.x -= acc[p][2]; v1.y -= acc[p][3];
+            dst[0] = v0; dst[1] = v1;
+          }
+        }
+      }
+    }
+    stamp();  // trailing computed (CTA 0)
+    cluster.sync();
+    stamp();  // trailing done
+  }
+  cluster.sync();
+  if (gtid == 0) *rank_out = s_rankA;
+  for (int e = tid; e < n * cw; e += kTailThreads) {
+    const int row = e / cw, cc = e % cw, col = col0 + cc;
+    const double v = Ws[(size_t)cc * ldt + row];
+    if (col < n) Wm[(size_t)row * ld + col] = v; else yv[row] = v;
+  }
+  stamp();  // end
+  if (prof && blockIdx.x == 0 && tid == 0) prof[prof_i] = 0ull;
+}
+
+}  // namespace mb

@@ -64,6 +64,8 @@ struct EngineBase {
   double rank_thr = 1e-11;
   long long launches = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;               // side branch of the update (k_blockdiag runs beside k_gram)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 template <class S>
@@ -76,6 +78,7 @@ struct Engine : EngineBase {
       *d_rank = nullptr, *d_keepclones = nullptr, *d_cmeff = nullptr;
   unsigned long long* d_csnap = nullptr;
   unsigned long long* d_prof = nullptr;
+  unsigned* d_done = nullptr;  // k_jac's CTA ticket counter
   S *d_obs = nullptr, *d_pfg = nullptr, *d_pfg_given = nullptr, *d_gamma = nullptr, *d_Xg = nullptr, *d_rg = nullptr,
     *d_Vg = nullptr, *d_taug = nullptr;
   double *d_Z = nullptr, *d_Yq = nullptr, *d_ur = nullptr, *d_G1p = nullptr, *d_G2p = nullptr, *d_D1 = nullptr, *d_D2 = nullptr,
@@ -121,6 +124,9 @@ struct Engine : EngineBase {
     const int cmax = 6 * Mmax;
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     CK(cudaMalloc(&d_st, sizeof(mb::DevState<S>)));
     CK(cudaMalloc(&d_P, sizeof(S) * (size_t)ldp * nmax));
     CK(cudaMalloc(&d_P2, sizeof(S) * (size_t)ldp * nmax));
@@ -138,6 +144,8 @@ struct Engine : EngineBase {
     CK(cudaMalloc(&d_cmeff, sizeof(int) * T));
     CK(cudaMalloc(&d_csnap, sizeof(unsigned long long)));
     CK(cudaMalloc(&d_prof, sizeof(unsigned long long) * 80));
+    CK(cudaMalloc(&d_done, sizeof(unsigned)));
+    CK(cudaMemsetAsync(d_done, 0, sizeof(unsigned), stream));
     CK(cudaMemsetAsync(d_prof, 0, sizeof(unsigned long long) * 80, stream));
     CK(cudaMalloc(&d_keep, sizeof(int) * nmax));
     CK(cudaMalloc(&d_m, sizeof(int) * 2));
@@ -178,8 +186,8 @@ struct Engine : EngineBase {
     CK(cudaFuncSetAttribute(mb::k_tri<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_jac<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_tail_fused<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_tail<S, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_tail<S, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_tail<S, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_tail<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaStreamSynchronize(stream));
     return 0;
   }
@@ -188,11 +196,14 @@ struct Engine : EngineBase {
     if (stream) cudaStreamSynchronize(stream);
     if (g_exec) cudaGraphExecDestroy(g_exec);
     void* dv[] = {d_st, d_P, d_P2, d_poses, d_poses2, d_off, d_idx, d_cm, d_tri, d_valid, d_src, d_accept, d_rows, d_rowoff,
-                  d_scratch, d_keep, d_m, d_keepclones, d_cmeff, d_csnap, d_prof, d_obs, d_pfg, d_pfg_given, d_gamma, d_Xg, d_rg, d_Vg, d_taug, d_Z, d_Yq,
+                  d_scratch, d_keep, d_m, d_keepclones, d_cmeff, d_csnap, d_prof, d_done, d_obs, d_pfg, d_pfg_given, d_gamma, d_Xg, d_rg, d_Vg, d_taug, d_Z, d_Yq,
                   d_ur, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_T2, d_R2, d_TP, d_S2, d_W, d_G, d_r2, d_y, d_dx, d_idiag};
     for (void* p : dv) if (p) cudaFree(p);
     void* hv[] = {h_off, h_idx, h_flags, h_mr, h_obs, h_pfg_in, h_pfg, h_gamma, h_st};
     for (void* p : hv) if (p) cudaFreeHost(p);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -328,6 +339,7 @@ struct Engine : EngineBase {
     a.pfg_given = (mode == MSCKF_B200_RESIDUALIZE) ? d_pfg_given : nullptr;
     a.accept = d_accept; a.gamma = d_gamma; a.rows = d_rows; a.Xg = d_Xg; a.rg = d_rg; a.Vg = d_Vg; a.taug = d_taug;
     a.Z = d_Z; a.Yq = d_Yq; a.ur = d_ur;
+    a.row_off = d_rowoff; a.m_out = d_m; a.done = d_done;
     a.prof = profile ? (d_prof + 40) : nullptr;
     const size_t pose_bytes = 16 + sizeof(S) * mb::kPoseStride * (size_t)M;
     if (mode != MSCKF_B200_RESIDUALIZE) {
@@ -343,13 +355,14 @@ struct Engine : EngineBase {
       mb::k_jac<S><<<N, mb::JT, jsmem, stream>>>(a, d_st, mode == MSCKF_B200_RESIDUALIZE ? 1 : 0);
       launches++;
       mark("k_jac");
-      mb::k_scan<<<1, 1024, 0, stream>>>(N, d_rows, d_rowoff, d_m);
-      launches++;
-      mark("k_scan");
       const double du = (double)h_st->u_var, dv = (double)h_st->v_var;
-      mb::k_blockdiag<S><<<M, 128, 0, stream>>>(N, d_off, d_idx, d_accept, d_Xg, d_rg, du, dv, d_D1, d_D2, d_bb);
+      // k_blockdiag and k_gram both depend on k_jac only: two branches (a fork / join in the captured graph)
+      cudaStream_t sb = profile ? stream : stream2;  // per-kernel event timing keeps everything on one stream
+      if (!profile) { CK(cudaEventRecord(ev_fork, stream)); CK(cudaStreamWaitEvent(stream2, ev_fork, 0)); }
+      mb::k_blockdiag<S><<<M, 128, 0, sb>>>(N, d_off, d_idx, d_accept, d_Xg, d_rg, du, dv, d_D1, d_D2, d_bb);
       launches++;
       mark("k_blockdiag");
+      if (!profile) CK(cudaEventRecord(ev_join, stream2));
       const int K = 3 * N;
       int nsplit = std::max(1, std::min(kMaxSplit, K / 96));
       int kchunk = (K + nsplit - 1) / nsplit;
@@ -359,6 +372,7 @@ struct Engine : EngineBase {
       mb::k_gram<<<dim3(ntile * (ntile + 1) / 2, nsplit), 256, 0, stream>>>(d_Z, d_Yq, K, c, kchunk, d_G1p, d_G2p);
       launches++;
       mark("k_gram");
+      if (!profile) CK(cudaStreamWaitEvent(stream, ev_join, 0));
       const int agrid = std::min(592, (n * n + 255) / 256);
       mb::k_assemble<<<agrid, 256, 0, stream>>>(n, ld, K, nsplit, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_Z, d_ur, d_m, d_T2, d_R2, d_r2);
       launches++;
@@ -368,9 +382,9 @@ struct Engine : EngineBase {
       launches++;
       mark("k_rows");
       const dim3 tg((n + 31) / 32, (n + 31) / 32);
-      mb::k_gemm_tp<S><<<tg, 64, 0, stream>>>(n, ld, d_T2, d_P, ldp, d_TP);
+      mb::k_gemm_tp<S><<<tg, mb::kGemmThreads, 0, stream>>>(n, ld, d_T2, d_P, ldp, d_TP);
       mark("k_gemm_tp");
-      mb::k_gemm_s<<<tg, 64, 0, stream>>>(n, ld, d_TP, d_T2, d_R2, d_S2);
+      mb::k_gemm_s<<<tg, mb::kGemmThreads, 0, stream>>>(n, ld, d_TP, d_T2, d_R2, d_S2);
       mark("k_gemm_s");
       launches += 2;
       // rank decision + Cholesky + substitution + covariance/state update: one cluster kernel (scratch for Gamma: d_G)
@@ -397,12 +411,12 @@ struct Engine : EngineBase {
                                 (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_dx, d_G /*scratch*/, pf));
         } else if (smem_for(32, false) <= kSmemBudget) {
           cfg.dynamicSmemBytes = smem_for(32, false);
-          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 32, false>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_R2 /*receives L (R'' is consumed by k_gemm_s)*/,
+          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 32>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_R2 /*receives L (R'' is consumed by k_gemm_s)*/,
                                 d_keep, d_idiag, rank_thr, d_rank, (const int*)d_m, (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_P, ldp, d_st,
                                 d_poses, d_dx, pf));
         } else if (smem_for(16, false) <= kSmemBudget) {
           cfg.dynamicSmemBytes = smem_for(16, false);
-          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 16, false>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_R2, d_keep, d_idiag, rank_thr, d_rank,
+          CK(cudaLaunchKernelEx(&cfg, mb::k_tail<S, 16>, n, ld, M, (const double*)d_T2, d_G, d_S2, d_R2, d_keep, d_idiag, rank_thr, d_rank,
                                 (const int*)d_m, (const double*)d_TP, (const double*)d_r2, d_W, d_y, d_P, ldp, d_st, d_poses, d_dx, pf));
         } else return fail(MSCKF_B200_ERR_CAPACITY, "k_tail shared memory");
       }
@@ -410,7 +424,7 @@ struct Engine : EngineBase {
       mark("k_tail");
       {
         const int nt32 = (n + 31) / 32;
-        mb::k_syrk<S><<<nt32 * (nt32 + 1) / 2, 64, 0, stream>>>(n, ld, d_W, d_P, ldp, d_m);
+        mb::k_syrk<S><<<nt32 * (nt32 + 1) / 2, mb::kGemmThreads, 0, stream>>>(n, ld, d_W, d_P, ldp, d_m);
         launches++;
         mark("k_syrk");
         mb::k_inject<S><<<1, 1024, sizeof(double) * n, stream>>>(n, ld, M, d_W, d_y, d_st, d_poses, d_dx, d_m, d_rank);

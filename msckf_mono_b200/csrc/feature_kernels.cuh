@@ -4,7 +4,7 @@
 //   k_jac     : one CTA per track: loop-A bookkeeping of marginalize() (msckf.h:352-399, incl. the p_f_G_vec index
 //               quirk of :419), calcResidual (:960-978), calcMeasJacobian (:905-958, left null space by 3 Householder
 //               reflectors of the column-pivoted QR of H_f), gatingTest (:1103-1124)
-//   k_scan    : ordered stacking offsets (msckf.h:433-445)
+//   (ordered stacking offsets, msckf.h:433-445: prefix sum by the last CTA of k_jac)
 // Clone poses are staged into shared memory with one TMA bulk copy per CTA.
 #pragma once
 #include "common.cuh"
@@ -34,6 +34,9 @@ struct FeatArgs {
   int* accept;         // [N]
   S* gamma;            // [N]
   int* rows;           // [N] rho_j = 2L-3
+  int* row_off;        // [N+1] ordered stacking (msckf.h:433-445): exclusive prefix sum of rows, by the last CTA of k_jac
+  int* m_out;          // total number of stacked rows m
+  unsigned* done;      // CTA ticket counter of k_jac (zero between launches)
   S* Xg;               // [sumL*12] H_x blocks (2x6 per observation)
   S* rg;               // [sumL*2]  residuals
   S* Vg;               // [sumL*2*3] Householder vectors of the null-space projection (unit lower trapezoid)
@@ -321,31 +324,48 @@ __device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
   v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
 }
 
+// Left-looking with a one-pivot look-ahead (same scheme as tf_factor in tail_fused.cuh): the bracket of column k + 1,
+//   br(i) = a_{i,k+1} - sum_{j<k} L_ij L_{k+1,j},  is formed while pivot k's rsqrt is in flight; pivot k + 1 then only
+// needs   t_i = br(i) - L_ik L_{k+1,k}   (one shuffle + one FMA).  A row's slot of column k + 1 is zeroed once its original
+// value sits in the bracket, so every not-yet-final entry of a 16-column chunk reads as zero: no masking.
 template <class S>
 __device__ __forceinline__ bool chol_warp(S* Yf, const S* dg, int rho, int lane) {
   const S d0 = (lane < rho) ? dg[lane] : S(1), d1 = (lane + 32 < rho) ? dg[lane + 32] : S(1);
   S* row0 = Yf + lane * kCholLd;
   S* row1 = Yf + (lane + 32) * kCholLd;
+  S br0 = (lane == 0) ? d0 : row0[0], br1 = row1[0];  // brackets of column 0: the original entries
+  if (lane > 0) row0[0] = S(0);
+  row1[0] = S(0);
+  S lp0 = S(0), lp1 = S(0);  // the rows' entries of the previous column
+  __syncwarp();
   for (int k = 0; k < rho; ++k) {
-    const S* prow = Yf + k * kCholLd;  // pivot row: final left of the diagonal, zero from the diagonal on
-    S a0[4] = {S(0), S(0), S(0), S(0)}, a1[4] = {S(0), S(0), S(0), S(0)};
-    for (int c0 = 0; c0 < k; c0 += 8) {
-      S p0[4], p1[4], x0[4], x1[4], y0[4], y1[4];
-      ld4(prow + c0, p0); ld4(prow + c0 + 4, p1);
-      ld4(row0 + c0, x0); ld4(row0 + c0 + 4, x1);
-      ld4(row1 + c0, y0); ld4(row1 + c0 + 4, y1);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { a0[u] += x0[u] * p0[u]; a1[u] += y0[u] * p0[u]; }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { a0[u] += x1[u] * p1[u]; a1[u] += y1[u] * p1[u]; }
-    }
-    const S s0 = ((lane == k) ? d0 : row0[k]) - ((a0[0] + a0[1]) + (a0[2] + a0[3]));
-    const S s1 = ((lane + 32 == k) ? d1 : row1[k]) - ((a1[0] + a1[1]) + (a1[2] + a1[3]));
-    const S piv = __shfl_sync(0xffffffffu, (k >= 32) ? s1 : s0, k & 31);
+    const S lk = __shfl_sync(0xffffffffu, (k >= 32) ? lp1 : lp0, k & 31);  // L_{k,k-1}
+    const S t0 = br0 - lp0 * lk, t1 = br1 - lp1 * lk;
+    const S piv = __shfl_sync(0xffffffffu, (k >= 32) ? t1 : t0, k & 31);
     if (!(piv > S(0))) return false;
+    // next bracket: loads before this pivot's stores; 16 columns per round trip
+    const int k1 = k + 1;  // <= rho <= 63: a valid row (the right-hand side is row rho)
+    const S* prow = Yf + k1 * kCholLd;
+    const S an0 = (lane == k1) ? d0 : row0[k1], an1 = (lane + 32 == k1) ? d1 : row1[k1];
+    S a0[4] = {S(0), S(0), S(0), S(0)}, a1[4] = {S(0), S(0), S(0), S(0)};
+    for (int c0 = 0; c0 < k; c0 += 16) {
+      S p[4][4], x[4][4], y[4][4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { ld4(prow + c0 + 4 * v, p[v]); ld4(row0 + c0 + 4 * v, x[v]); ld4(row1 + c0 + 4 * v, y[v]); }
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a0[u] += x[v][u] * p[v][u]; a1[u] += y[v][u] * p[v][u]; }
+    }
     const S inv = trsqrt<S>(piv);
-    if (lane > k && lane <= rho) row0[k] = s0 * inv;
-    if (lane + 32 > k && lane + 32 <= rho) row1[k] = s1 * inv;
+    const S l0 = (lane > k) ? t0 * inv : S(0), l1 = (lane + 32 > k) ? t1 * inv : S(0);
+    br0 = an0 - ((a0[0] + a0[1]) + (a0[2] + a0[3]));
+    br1 = an1 - ((a1[0] + a1[1]) + (a1[2] + a1[3]));
+    if (lane > k && lane <= rho) row0[k] = l0;
+    if (lane + 32 > k && lane + 32 <= rho) row1[k] = l1;
+    if (lane > k1) row0[k1] = S(0);      // the original values live in the brackets now
+    if (lane + 32 > k1) row1[k1] = S(0);
+    lp0 = l0; lp1 = l1;
     __syncwarp();
   }
   return true;
@@ -357,6 +377,34 @@ __host__ __device__ inline size_t jac_smem_bytes(int L, int M) {
   // Yf 64 x 68 + dg 64 (S): the single-warp gate Cholesky's row-major copy
   return 16 + sizeof(S) * kPoseStride * (size_t)M + 16 + sizeof(double) * 6 * (size_t)L +
          sizeof(S) * ((size_t)32 * L + (size_t)L * (2 * L + 1)) + 32 + sizeof(S) * ((size_t)kCholRows * kCholLd + kCholRows);
+}
+
+// Ordered stacking (msckf.h:433-445): the exclusive prefix sum of the accepted blocks' row counts, computed by whichever
+// CTA of k_jac finishes last (ticket counter) -- a separate 1-CTA kernel for 300 integers cost 8 us of launch latency.
+template <class S>
+__device__ __forceinline__ void jac_finish(const FeatArgs<S>& a) {
+  __shared__ int s_last;
+  __shared__ int s_part[JT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __syncthreads();
+  if (tid == 0) { __threadfence(); s_last = (atomicAdd(a.done, 1u) == gridDim.x - 1) ? 1 : 0; }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int N = a.n_tracks, per = (N + JT - 1) / JT;
+  const int b = min(N, tid * per), e = min(N, b + per);
+  int sum = 0;
+  for (int k = b; k < e; ++k) sum += __ldcg(a.rows + k);
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) s_part[warp] = incl;
+  __syncthreads();
+  int run = incl - sum;
+  for (int w = 0; w < warp; ++w) run += s_part[w];
+  for (int k = b; k < e; ++k) { a.row_off[k] = run; run += __ldcg(a.rows + k); }
+  if (tid == JT - 1) { a.row_off[N] = run; *a.m_out = run; }
+  if (tid == 0) *a.done = 0u;
 }
 
 // calcResidual + calcMeasJacobian + gatingTest for one feature per CTA (JT threads), with loop A's bookkeeping
@@ -452,6 +500,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   if (!valid) {  // not residualised: contributes nothing
     for (int k = tid; k < 3 * c; k += JT) { Zr[k] = 0.0; Yr[k] = 0.0; }
     if (tid == 0) { a.accept[t] = 0; a.gamma[t] = S(0); a.rows[t] = 0; a.ur[3 * t] = a.ur[3 * t + 1] = a.ur[3 * t + 2] = 0.0; }
+    jac_finish(a);
     return;
   }
   // ------------------------------------------------------------------ shared-memory carve-up
@@ -872,30 +921,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   }
   stamp();  // outputs
   if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[prof_i] = 0ull;
-}
-
-// Ordered stacking (msckf.h:433-445): exclusive prefix sum of the accepted blocks' row counts.
-__global__ void k_scan(int N, const int* rows, int* row_off /*[N+1]*/, int* m_out) {
-  __shared__ int s_scan[1024];
-  const int tid = threadIdx.x;
-  int carry = 0;
-  for (int base = 0; base < N; base += 1024) {
-    const int k = base + tid;
-    const int v = (k < N) ? rows[k] : 0;
-    s_scan[tid] = v;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      int t = (tid >= o) ? s_scan[tid - o] : 0;
-      __syncthreads();
-      s_scan[tid] += t;
-      __syncthreads();
-    }
-    if (k < N) row_off[k] = carry + s_scan[tid] - v;
-    const int tot = s_scan[1023];
-    __syncthreads();
-    carry += tot;
-  }
-  if (tid == 0) { row_off[N] = carry; *m_out = carry; }
+  jac_finish(a);
 }
 
 }  // namespace mb

@@ -168,7 +168,7 @@ __device__ __forceinline__ void tc_substitute(int n, int ld, int C, int crank, i
   }
 }
 
-template <class S, int NB, bool FUSED>
+template <class S, int NB>
 __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, const double* __restrict__ T2, double* __restrict__ G,
                                                       double* __restrict__ A, double* __restrict__ Lout, int* __restrict__ keep,
                                                       double* __restrict__ idiag,
@@ -188,13 +188,6 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
     }
   };
   stamp();
-  auto dstamp = [&](int kb, int i) {  // fine-grained stamps of the first block's phases 2 and 3 (CTA 0, thread 0): prof[64 + i]
-    if (prof && kb == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) : : "memory");
-      prof[64 + i] = t;
-    }
-  };
   const int crank = (int)cluster.block_rank();
   const int C = (int)cluster.num_blocks();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -208,7 +201,6 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
   double* d0 = PT_G + (size_t)NB * ldt;      // [n] original diagonal of Gamma (CTA 0); later keep flags
   double* idg = d0 + ((n + 1) & ~1);         // [NB] 1 / diag of the current block of G's factor (0 = dropped)
   double* ida = idg + NB;                    // [NB] same for A
-  double* idaEnd = ida + NB;
   __shared__ int s_rank;
   const int m = *m_in;
   const bool full = m <= n;  // all rows explicit and orthonormal: Gamma = I_m, nothing to decide, G untouched
@@ -241,24 +233,6 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
   }
   __syncthreads();
   // ---------------------------------------------------------------- blocked rank-revealing Cholesky (G decides, A follows)
-  // FUSED: the forward substitution W = L^-1 [T''P | r''] rides along: every CTA keeps its share of the RHS columns as
-  // rows of Ws (shared memory) and treats them as extra panel rows -- solved against the diagonal block in phase 2,
-  // updated with the staged panel in phase 3.  The factor itself is then never needed again (no Lout, no second sweep).
-  const int ncol = n + 1;
-  const int per = (ncol + C - 1) / C;          // RHS columns per CTA (FUSED: <= NB)
-  const int col0 = crank * per, cw = max(0, min(per, ncol - col0));
-  const int ncw4 = (cw + 3) / 4;
-  double* Ws = idaEnd;                         // [NB][ldt]  FUSED only: row c = RHS column col0 + c
-  double* XT = Ws + (size_t)NB * ldt;          // [NB][NB]   FUSED only: solved block of the W rows, transposed
-  if constexpr (FUSED) {
-    for (int e = tid; e < NB * n; e += kTailThreads) {
-      const int k = e / NB, c = e % NB, col = col0 + c;
-      double v = 0.0;
-      if (c < cw) v = (col < n) ? TP[(size_t)k * ld + col] : r2[k];
-      Ws[(size_t)c * ldt + k] = v;
-    }
-    for (int e = tid; e < NB * (ldt - n); e += kTailThreads) Ws[(size_t)(e / (ldt - n)) * ldt + n + e % (ldt - n)] = 0.0;
-  }
   for (int kb = 0; kb < n; kb += NB) {
     const int nb = min(NB, n - kb);
     const int r0 = kb + nb;
@@ -269,38 +243,38 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
       __syncthreads();
       if (warp == 0) {
         int rank_now = s_rank;
-        // lane = row.  The lane's own row of both matrices lives in registers (static indices: the k/j loops are fully
-        // unrolled); the pivot row is read from shared memory as a broadcast (one wavefront, no bank conflicts).
-        double ra[NB], rg[NB];
+        for (int k = 0; k < nb; ++k) {
+          // left-looking: column k of both factors from the already final columns j < k (reads only, no RMW chain)
+          double sa = 0.0, sg = 0.0;
+          if (lane >= k && lane < nb) {
+            sa = DA[lane * LD + k];
+            if (!full) sg = DG[lane * LD + k];
+            double a4[4] = {0.0, 0.0, 0.0, 0.0}, g4[4] = {0.0, 0.0, 0.0, 0.0};  // 4 partial sums: short FMA chains
+            int j = 0;
+            for (; j + 4 <= k; j += 4) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) { ra[j] = DA[lane * LD + j]; rg[j] = full ? 0.0 : DG[lane * LD + j]; }
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-          if (k < nb) {  // uniform
-            // left-looking: column k from the already final columns j < k
-            double a4[4] = {0.0, 0.0, 0.0, 0.0}, g4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int j = 0; j < k; ++j) {
-              a4[j & 3] += ra[j] * DA[k * LD + j];
-              if (!full) g4[j & 3] += rg[j] * DG[k * LD + j];
+              for (int u = 0; u < 4; ++u) {
+                a4[u] += DA[lane * LD + j + u] * DA[k * LD + j + u];
+                if (!full) g4[u] += DG[lane * LD + j + u] * DG[k * LD + j + u];
+              }
             }
-            const double sa = ra[k] - ((a4[0] + a4[1]) + (a4[2] + a4[3]));
-            const double sg = rg[k] - ((g4[0] + g4[1]) + (g4[2] + g4[3]));
-            const double pa = __shfl_sync(0xffffffffu, sa, k), pg = full ? 1.0 : __shfl_sync(0xffffffffu, sg, k);
-            const double dk0 = d0[kb + k];
-            const bool drop = !(dk0 > 0.0) || !(pg > thr * dk0) || rank_now >= rank_cap || !(pa > 0.0);
-            if (!drop) rank_now++;
-            const double ig = drop ? 0.0 : rsqrt(pg), ia = drop ? 0.0 : rsqrt(pa);
-            // lanes below the pivot: their entry of column k; the pivot lane: the diagonal; lanes above: untouched
-            double va = (lane > k) ? sa * ia : ((lane == k) ? (drop ? 1.0 : pa * ia) : ra[k]);
-            double vg = (lane > k) ? sg * ig : ((lane == k) ? (drop ? 1.0 : pg * ig) : rg[k]);
-            ra[k] = va; rg[k] = vg;
-            // dropped index: its row left of the diagonal is removed from the factor (lane k's registers are dead now)
-            if (drop && lane < k) { DA[k * LD + lane] = 0.0; DG[k * LD + lane] = 0.0; }
-            if (lane >= k && lane < nb) { DA[lane * LD + k] = va; if (!full) DG[lane * LD + k] = vg; }
-            if (lane == k) { ida[k] = ia; idg[k] = ig; }
-            __syncwarp();
+            for (; j < k; ++j) { a4[0] += DA[lane * LD + j] * DA[k * LD + j]; if (!full) g4[0] += DG[lane * LD + j] * DG[k * LD + j]; }
+            sa -= (a4[0] + a4[1]) + (a4[2] + a4[3]);
+            sg -= (g4[0] + g4[1]) + (g4[2] + g4[3]);
           }
+          const double pa = __shfl_sync(0xffffffffu, sa, k), pg = full ? 1.0 : __shfl_sync(0xffffffffu, sg, k);
+          const double dk0 = d0[kb + k];
+          const bool drop = !(dk0 > 0.0) || !(pg > thr * dk0) || rank_now >= rank_cap || !(pa > 0.0);
+          if (!drop) rank_now++;
+          const double ig = drop ? 0.0 : rsqrt(pg), ia = drop ? 0.0 : rsqrt(pa);
+          __syncwarp();
+          if (lane > k && lane < nb) { DA[lane * LD + k] = sa * ia; if (!full) DG[lane * LD + k] = sg * ig; }
+          if (lane == k) {
+            DA[k * LD + k] = drop ? 1.0 : pa * ia; DG[k * LD + k] = drop ? 1.0 : pg * ig;
+            ida[k] = ia; idg[k] = ig;
+          }
+          if (drop && lane < k) { DA[k * LD + lane] = 0.0; DG[k * LD + lane] = 0.0; }
+          __syncwarp();
         }
         if (lane == 0) s_rank = rank_now;
         for (int k = nb + lane; k < NB; k += 32) { ida[k] = 0.0; idg[k] = 0.0; }
@@ -310,16 +284,15 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
         const int i = e / nb, j = e % nb;
         if (j <= i) {
           A[(size_t)(kb + i) * ld + kb + j] = DA[i * LD + j];     // read by the other CTAs in phase 2
-          if constexpr (!FUSED) Lout[(size_t)(kb + i) * ld + kb + j] = DA[i * LD + j];  // the factor itself (A's panels stay
+          Lout[(size_t)(kb + i) * ld + kb + j] = DA[i * LD + j];  // the factor itself (A's panels stay
           if (!full) G[(size_t)(kb + i) * ld + kb + j] = DG[i * LD + j];  // untouched: the whole cluster is reading them)
         }
       }
       if (tid < nb) { keep[kb + tid] = ida[tid] != 0.0 ? 1 : 0; idiag[kb + tid] = ida[tid]; idiag[n + kb + tid] = idg[tid]; }
     }
     stamp();  // diagonal block done
-    if (!FUSED && r0 >= n) break;  // last block: nothing below
+    if (r0 >= n) break;  // last block: nothing below
     cluster.sync();
-    dstamp(kb, 0);
     // phase 2 (every CTA, redundantly): all panel rows below the block -> transposed shared panel (CTA 0 also -> global)
     if (crank != 0) {
       if (!full) tc_load_diag<NB>(DG, G, ld, kb, nb, tid);
@@ -327,18 +300,11 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
       if (tid < NB) { ida[tid] = (tid < nb) ? idiag[kb + tid] : 0.0; idg[tid] = (tid < nb) ? idiag[n + kb + tid] : 0.0; }
     }
     __syncthreads();
-    dstamp(kb, 1);
     const int nr = n - r0;
-    if constexpr (FUSED) {  // the W rows of this CTA: the last warp(s), one thread per row
-      const int c = kTailThreads - 1 - tid;
-      if (c < NB) tc_w_row<NB>(Ws + (size_t)c * ldt + kb, nb, DA, ida, XT, c);
-    }
     for (int row = r0 + tid; row < n; row += kTailThreads) {
-      tc_panel_row<NB>(A, ld, row, kb, nb, DA, ida, PT_A, ldt, row - r0, (!FUSED && crank == 0) ? Lout : nullptr);
+      tc_panel_row<NB>(A, ld, row, kb, nb, DA, ida, PT_A, ldt, row - r0, crank == 0 ? Lout : nullptr);
       if (!full) tc_panel_row<NB>(G, ld, row, kb, nb, DG, idg, PT_G, ldt, row - r0, nullptr);
     }
-    dstamp(kb, 2);
-    if (r0 >= n) break;  // (FUSED) last block: the W rows are complete
     {  // zero the tail of the padded rows so that partial tiles read zeros
       const int nrp = (nr + 3) & ~3;
       for (int e = tid; e < (nrp - nr) * NB; e += kTailThreads) {
@@ -350,12 +316,12 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
     __syncthreads();
     stamp();  // panel done
     // phase 3 (cluster-wide): trailing update, 4x4 register tiles on the transposed panel.  Work items: the lower-triangle
-    // tiles of A, then of G, dealt round-robin to the CTAs; then (FUSED) this CTA's own W tiles.
+    // tiles of A, then of G, dealt round-robin to the CTAs.
     {
       const int nt = (nr + 3) / 4, ntile = nt * (nt + 1) / 2;
       const int nitems = full ? ntile : 2 * ntile;
       const int mine = (nitems > crank) ? (nitems - crank + C - 1) / C : 0;
-      const int nloc = mine + (FUSED ? ncw4 * nt : 0);
+      const int nloc = mine;
       for (int q = tid; q < nloc; q += kTailThreads) {
         if (q < mine) {
           const int it = crank + C * q;
@@ -374,7 +340,6 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
             }
           double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
           tc_tile_4x4(PT, PT, ldt, ldt, 4 * ti, 4 * tj, NB, acc);
-          if (q == tid) dstamp(kb, 3);
 #pragma unroll
           for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -382,18 +347,6 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
               const int i = 4 * ti + p, i2 = 4 * tj + qq;
               if (i < nr && i2 <= i) Mat[(size_t)i * ld + i2] = old[p][qq] - acc[p][qq];
             }
-          if (q == tid) dstamp(kb, 4);
-        } else if constexpr (FUSED) {
-          const int w = q - mine, c4 = w % ncw4, ti = w / ncw4;
-          double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-          tc_tile_4x4(XT, PT_A, NB, ldt, 4 * c4, 4 * ti, NB, acc);
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            double2* dst = reinterpret_cast<double2*>(Ws + (size_t)(4 * c4 + p) * ldt + r0 + 4 * ti);
-            double2 v0 = dst[0], v1 = dst[1];
-            v0.x -= acc[p][0]; v0.y -= acc[p][1]; v1.x -= acc[p][2]; v1.y -= acc[p][3];
-            dst[0] = v0; dst[1] = v1;
-          }
         }
       }
     }
@@ -403,15 +356,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
   }
   cluster.sync();
   if (gtid == 0) *rank_out = s_rank;
-  if constexpr (FUSED) {
-    stamp();  // factorisation + substitution complete
-    __syncthreads();
-    for (int e = tid; e < n * cw; e += kTailThreads) {
-      const int row = e / cw, cc = e % cw, col = col0 + cc;
-      const double v = Ws[(size_t)cc * ldt + row];
-      if (col < n) Wm[(size_t)row * ld + col] = v; else yv[row] = v;
-    }
-  } else {
+  {
     // dropped rows: clear what earlier panels wrote left of the diagonal
     for (size_t e = gtid; e < (size_t)n * n; e += gthreads) {
       const int k = (int)(e / n), cc = (int)(e % n);

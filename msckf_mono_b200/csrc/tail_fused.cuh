@@ -80,35 +80,75 @@ __device__ __forceinline__ void tf_load_diag(double* D, double* dg, const double
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory");                 \
     dprof[6 * (k - 20) + (i)] = t_;                                                    \
   }
+// Hand-off of per-pivot results between warps of one CTA through shared memory: the producer's lanes store their data,
+// __syncwarp() orders them before lane 0's volatile flag store; the consumer polls the flag, then reads the data.
+// Shared memory has no cache and a warp's shared-memory instructions are performed in issue order, so no MEMBAR is
+// needed (a __threadfence_block() per pivot costs ~113 cycles on each side, measured; the compiler barrier keeps the order).
+__device__ __forceinline__ void tf_publish(int* step, int v, int lane) {
+  __syncwarp();
+  if (lane == 0) *reinterpret_cast<volatile int*>(step) = v;
+}
+__device__ __forceinline__ void tf_wait(const int* step, int k) {
+  while (*reinterpret_cast<const volatile int*>(step) <= k) { }
+  asm volatile("" ::: "memory");
+}
+
+// One warp factorises a 32 x 32 block in place (lane = row i, strictly lower storage).  Left-looking with a one-pivot
+// look-ahead, so that only   shuffle -> FMA -> shuffle -> rsqrt -> multiply   sits on the dependent chain of a pivot:
+//   br_k(i) = a_ik - sum_{j<k-1} L_ij L_kj        is formed during pivot k-1 (it needs nothing pivot k-1 produces),
+//   t_i     = br_k(i) - L_{i,k-1} L_{k,k-1}       finishes column k with one FMA (L_{k,k-1} by shuffle from lane k),
+//   L_ik    = t_i / sqrt(t_k).
+// The loads and FMAs of br_{k+1} are independent of pivot k's rsqrt and sit in the same basic block, so the scheduler
+// overlaps them with it.  A row's slot of column k+1 is zeroed once its original value is in the bracket; together with
+// the strictly lower storage this makes every not-yet-final entry of a 16-column chunk read as zero: no masking.
+// decide(k, pivot) -> drop; inv[k] = 1 / L_kk (0 for a dropped index, whose row and column leave the factor).  After
+// pivot k, *step = k + 1 (followers poll it).
 template <class Decide>
 __device__ __forceinline__ void tf_factor(double* D, double dself, double* inv, int nb, int lane, int* step, Decide decide,
                                           unsigned long long* dprof = nullptr) {
   constexpr int LD = kFLD;
   double* row = D + lane * LD;
+  double br = (lane == 0) ? dself : row[0];  // bracket of column 0: the original entry
+  if (lane > 0) row[0] = 0.0;
+  double lprev = 0.0;                        // this row's entry of the previous column
+  __syncwarp();
   for (int k = 0; k < nb; ++k) {
     TF_DSTAMP(0)
-    double a4[4] = {0.0, 0.0, 0.0, 0.0};
-    const double* prow = D + k * LD;  // the pivot row is zero from its diagonal on: no masking needed
-    for (int j0 = 0; j0 < k; j0 += 8) {
-      double p[8], x[8];
-      tf_ld8(prow + j0, p);
-      tf_ld8(row + j0, x);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) a4[u & 3] += x[u] * p[u];
-    }
+    const double lk = __shfl_sync(0xffffffffu, lprev, k);  // L_{k,k-1}
+    const double t = br - lprev * lk;
+    const double pv = __shfl_sync(0xffffffffu, t, k);
     TF_DSTAMP(1)
-    const double sv = ((lane == k) ? dself : row[k]) - ((a4[0] + a4[1]) + (a4[2] + a4[3]));
-    const double pv = __shfl_sync(0xffffffffu, sv, k);
-    TF_DSTAMP(2)
     const bool drop = decide(k, pv);
-    TF_DSTAMP(3)
+    TF_DSTAMP(2)
+    // ---- next bracket: loads first (before this pivot's stores), 16 columns per round trip, FMAs on 8 accumulators
+    const int k1 = (k + 1 < kFB) ? k + 1 : k;  // (the last pivot computes a dummy bracket)
+    const double* prow = D + k1 * LD;
+    const double anext = (lane == k1) ? dself : row[k1];
+    double a8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (16 * h < k) {
+        double p0[8], x0[8], p1[8], x1[8];
+        tf_ld8(prow + 16 * h, p0); tf_ld8(row + 16 * h, x0);
+        tf_ld8(prow + 16 * h + 8, p1); tf_ld8(row + 16 * h + 8, x1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a8[u] += x0[u] * p0[u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a8[u] += x1[u] * p1[u];
+      }
+    }
+    // ---- this pivot
     const double iv = drop ? 0.0 : tf_rsqrt(pv);
-    if (lane > k && lane < nb) row[k] = sv * iv;
-    if (drop && lane < k) D[k * LD + lane] = 0.0;
+    const double lnew = (lane > k) ? t * iv : 0.0;
+    br = anext - (((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7])));
+    TF_DSTAMP(3)
+    if (lane > k && lane < nb) row[k] = lnew;
+    if (lane > k1) row[k1] = 0.0;                  // its original value lives in br now
+    if (drop && lane < k) D[k * LD + lane] = 0.0;  // a dropped index leaves the factor
     if (lane == k) inv[k] = iv;
+    lprev = lnew;
     TF_DSTAMP(4)
-    __syncwarp();
-    if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(step) = k + 1; }
+    tf_publish(step, k + 1, lane);
     TF_DSTAMP(5)
   }
 }
@@ -118,16 +158,23 @@ __device__ __forceinline__ void tf_factor(double* D, double dself, double* inv, 
 __device__ __forceinline__ void tf_invert(const double* Lf, const double* inv, double* LI, int nb, int lane, const int* step) {
   constexpr int LD = kFLD;
   for (int k = 0; k < nb; ++k) {
-    while (*reinterpret_cast<const volatile int*>(step) <= k) { }
-    __threadfence_block();
-    double a4[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int j0 = 0; j0 < k; j0 += 8) {  // L's row k is zero from the diagonal on
-      double p[8];
-      tf_ld8(Lf + k * LD + j0, p);
+    tf_wait(step, k);
+    double a8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a4[u & 3] += p[u] * LI[(j0 + u) * LD + lane];
+    for (int h = 0; h < 2; ++h) {  // L's row k is zero from the diagonal on; 16 columns per round trip
+      if (16 * h < k) {
+        double p0[8], p1[8], y0[8], y1[8];
+        tf_ld8(Lf + k * LD + 16 * h, p0);
+        tf_ld8(Lf + k * LD + 16 * h + 8, p1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { y0[u] = LI[(16 * h + u) * LD + lane]; y1[u] = LI[(16 * h + 8 + u) * LD + lane]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a8[u] += p0[u] * y0[u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a8[u] += p1[u] * y1[u];
+      }
     }
-    const double acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    const double acc = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
     const double ik = *reinterpret_cast<const volatile double*>(inv + k);
     LI[k * LD + lane] = (lane <= k) ? ik * ((lane == k ? 1.0 : 0.0) - acc) : 0.0;
   }
@@ -185,8 +232,8 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(int n, int ld, doub
     return;
   }
   const int ncol = n + 1;
-  const int per = (ncol + C - 1) / C;  // RHS columns per CTA (<= 32)
-  const int col0 = crank * per, cw = max(0, min(per, ncol - col0));
+  const int per = (ncol + C - 2) / (C - 1);  // RHS columns per CTA (<= 32); CTA 0 (the diagonal blocks) takes none
+  const int col0 = (crank - 1) * per, cw = (crank == 0) ? 0 : max(0, min(per, ncol - col0));
   const int ncw4 = (cw + 3) / 4;
   // ---------------------------------------------------------------- Gamma = [[I_h, H_h], [H_h^T, Lambda]]: T'' already
   // holds H_h (rows < 15) and Lambda; only the lower triangle is read below, so patching the first 15 columns suffices
@@ -211,59 +258,66 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(int n, int ld, doub
   }
   __syncthreads();
   // ---------------------------------------------------------------- blocked rank-revealing Cholesky (G decides, A follows)
+  // CTA 0 factorises diagonal blocks: four warps on four sub-partitions -- G's factor (decides), A's factor (follows G's
+  // decision pivot by pivot) and the inverses of the two factors one pivot behind.  The blocks (strictly lower part in
+  // DG / DA, diagonals in dgG / dgA) are in shared memory when this is called; the inverses end up in LIG / LIA and in
+  // the L2 scratch for the other CTAs.  Block 0 is factorised up front; block kb + 1 is factorised by CTA 0 WHILE the
+  // other CTAs run the trailing update of block kb (it only needs the leading 32 x 32 tile of that update, which CTA 0
+  // forms itself from the panel).
+  auto factor_block = [&](int kb, int nb, bool stamps) {
+    for (int e = tid; e < NB * LD; e += kTailThreads) { LIA[e] = 0.0; LIG[e] = 0.0; }
+    if (tid == 0) { s_stepA = 0; s_stepG = 0; }
+    __syncthreads();
+    if (stamps && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[76] = t_; }
+    if (warp == 3 && !full) {
+      int rk = s_rankG;
+      tf_factor(DG, dgG[lane], idg, nb, lane, &s_stepG, [&](int k, double pv) {
+        const double dk0 = d0[kb + k];
+        const bool drop = !(dk0 > 0.0) || !(pv > thr * dk0) || rk >= rank_cap;
+        if (!drop) rk++;
+        return drop;
+      });
+      if (lane == 0) s_rankG = rk;
+    } else if (warp == 0) {
+      int rk = s_rankA;
+      tf_factor(DA, dgA[lane], ida, nb, lane, &s_stepA, [&](int k, double pv) {
+        bool drop;
+        if (full) drop = !(d0[kb + k] > 0.0) || rk >= rank_cap;
+        else {
+          tf_wait(&s_stepG, k);
+          drop = *reinterpret_cast<volatile double*>(idg + k) == 0.0;
+        }
+        drop = drop || !(pv > 0.0);
+        if (!drop) rk++;
+        return drop;
+      }, stamps ? prof + 64 : nullptr);
+      if (lane == 0) s_rankA = rk;
+      for (int k = nb + lane; k < NB; k += 32) { ida[k] = 0.0; idg[k] = 0.0; }
+    } else if (warp == 1) {
+      tf_invert(DA, ida, LIA, nb, lane, &s_stepA);
+    } else if (warp == 2 && !full) {
+      tf_invert(DG, idg, LIG, nb, lane, &s_stepG);
+    }
+    __syncthreads();
+    if (stamps && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[77] = t_; }
+    // the inverses go to the other CTAs through L2 (a DSMEM push of 2 x 8.7 KB to 7 CTAs runs at ~20 B/clk: 3 us)
+    for (int e = tid; e < NB * LD / 2; e += kTailThreads) {
+      reinterpret_cast<double2*>(Lsc)[e] = reinterpret_cast<const double2*>(LIA)[e];
+      if (!full) reinterpret_cast<double2*>(Lsc + NB * LD)[e] = reinterpret_cast<const double2*>(LIG)[e];
+    }
+  };
+  if (crank == 0) {
+    const int nb0 = min(NB, n);
+    if (!full) tf_load_diag(DG, dgG, G, ld, 0, nb0, tid);
+    tf_load_diag(DA, dgA, A, ld, 0, nb0, tid);
+    factor_block(0, nb0, prof != nullptr);
+  }
+  stamp();  // diagonal block 0 done
   for (int kb = 0; kb < n; kb += NB) {
     const int nb = min(NB, n - kb);
     const int r0 = kb + nb;
     const int nr = n - r0;
-    // phase 1 (CTA 0): the diagonal blocks, four warps on four sub-partitions: G's factor (decides), A's factor (follows
-    // G's decision pivot by pivot), and the inverses of the two factors one pivot behind.
-    if (crank == 0) {
-      if (!full) tf_load_diag(DG, dgG, G, ld, kb, nb, tid);
-      tf_load_diag(DA, dgA, A, ld, kb, nb, tid);
-      for (int e = tid; e < NB * LD; e += kTailThreads) { LIA[e] = 0.0; LIG[e] = 0.0; }
-      if (tid == 0) { s_stepA = 0; s_stepG = 0; }
-      __syncthreads();
-      if (prof && kb == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[76] = t_; }
-      if (warp == 3 && !full) {
-        int rk = s_rankG;
-        tf_factor(DG, dgG[lane], idg, nb, lane, &s_stepG, [&](int k, double pv) {
-          const double dk0 = d0[kb + k];
-          const bool drop = !(dk0 > 0.0) || !(pv > thr * dk0) || rk >= rank_cap;
-          if (!drop) rk++;
-          return drop;
-        });
-        if (lane == 0) s_rankG = rk;
-      } else if (warp == 0) {
-        int rk = s_rankA;
-        tf_factor(DA, dgA[lane], ida, nb, lane, &s_stepA, [&](int k, double pv) {
-          bool drop;
-          if (full) drop = !(d0[kb + k] > 0.0) || rk >= rank_cap;
-          else {
-            while (*reinterpret_cast<volatile int*>(&s_stepG) <= k) { }
-            __threadfence_block();
-            drop = *reinterpret_cast<volatile double*>(idg + k) == 0.0;
-          }
-          drop = drop || !(pv > 0.0);
-          if (!drop) rk++;
-          return drop;
-        }, (prof && kb == 0) ? prof + 64 : nullptr);
-        if (lane == 0) s_rankA = rk;
-        for (int k = nb + lane; k < NB; k += 32) { ida[k] = 0.0; idg[k] = 0.0; }
-      } else if (warp == 1) {
-        tf_invert(DA, ida, LIA, nb, lane, &s_stepA);
-      } else if (warp == 2 && !full) {
-        tf_invert(DG, idg, LIG, nb, lane, &s_stepG);
-      }
-      __syncthreads();
-      if (prof && kb == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[77] = t_; }
-      // the inverses go to the other CTAs through L2 (a DSMEM push of 2 x 8.7 KB to 7 CTAs runs at ~20 B/clk: 3 us)
-      for (int e = tid; e < NB * LD / 2; e += kTailThreads) {
-        reinterpret_cast<double2*>(Lsc)[e] = reinterpret_cast<const double2*>(LIA)[e];
-        if (!full) reinterpret_cast<double2*>(Lsc + NB * LD)[e] = reinterpret_cast<const double2*>(LIG)[e];
-      }
-    }
-    stamp();  // diagonal block done
-    cluster.sync();
+    cluster.sync();  // inverses of block kb in L2; trailing update of block kb - 1 complete
     // phase 2: the panel below the block, X = rows * Linv^T.  Rows are dealt to the CTAs in contiguous chunks (an even
     // number of rows each); lane = local row, warp w computes columns w, w + 8, w + 16, w + 24; the results go to a scratch
     // panel in L2 that every CTA reads back after the barrier.  The W rows of this CTA are solved the same way (local).
@@ -271,10 +325,18 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(int n, int ld, doub
     const int i0 = crank * chunk;
     const int nloc = max(0, min(chunk, nr - i0));
     {
-      if (crank != 0) {
-        for (int e = tid; e < NB * LD / 2; e += kTailThreads) {
-          reinterpret_cast<double2*>(LIA)[e] = __ldcg(reinterpret_cast<const double2*>(Lsc) + e);
-          if (!full) reinterpret_cast<double2*>(LIG)[e] = __ldcg(reinterpret_cast<const double2*>(Lsc + NB * LD) + e);
+      if (crank != 0) {  // all loads in flight before the first store
+        constexpr int NE = NB * LD / 2, NI = (NE + kTailThreads - 1) / kTailThreads;
+        double2 va[NI], vg[NI];
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+          const int e = tid + u * kTailThreads;
+          if (e < NE) { va[u] = __ldcg(reinterpret_cast<const double2*>(Lsc) + e); if (!full) vg[u] = __ldcg(reinterpret_cast<const double2*>(Lsc + NB * LD) + e); }
+        }
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+          const int e = tid + u * kTailThreads;
+          if (e < NE) { reinterpret_cast<double2*>(LIA)[e] = va[u]; if (!full) reinterpret_cast<double2*>(LIG)[e] = vg[u]; }
         }
       }
       for (int e = tid; e < NB * NB; e += kTailThreads) {
@@ -328,10 +390,27 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(int n, int ld, doub
     cluster.sync();
     {
       const int nr2 = (nr + 1) >> 1;  // 16-byte loads; an odd last column picks up the (finite) neighbour, zeroed below
-      for (int e = tid; e < NB * nr2; e += kTailThreads) {
-        const int j = e / nr2, l2 = 2 * (e % nr2);
-        *reinterpret_cast<double2*>(PT_A + (size_t)j * ldt + l2) = __ldcg(reinterpret_cast<const double2*>(Psc + (size_t)j * ldt + l2));
-        if (!full) *reinterpret_cast<double2*>(PT_G + (size_t)j * ldt + l2) = __ldcg(reinterpret_cast<const double2*>(Psc + (size_t)(NB + j) * ldt + l2));
+      const int tot = NB * nr2;
+      for (int e0 = tid; e0 < tot; e0 += 4 * kTailThreads) {  // 4 (8) loads in flight per thread before the first store
+        double2 va[4], vg[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * kTailThreads;
+          if (e < tot) {
+            const int j = e / nr2, l2 = 2 * (e % nr2);
+            va[u] = __ldcg(reinterpret_cast<const double2*>(Psc + (size_t)j * ldt + l2));
+            if (!full) vg[u] = __ldcg(reinterpret_cast<const double2*>(Psc + (size_t)(NB + j) * ldt + l2));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * kTailThreads;
+          if (e < tot) {
+            const int j = e / nr2, l2 = 2 * (e % nr2);
+            *reinterpret_cast<double2*>(PT_A + (size_t)j * ldt + l2) = va[u];
+            if (!full) *reinterpret_cast<double2*>(PT_G + (size_t)j * ldt + l2) = vg[u];
+          }
+        }
       }
       __syncthreads();
       const int nrp = (nr + 3) & ~3;  // zero the tail of the padded rows so that partial tiles read zeros
@@ -343,22 +422,45 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(int n, int ld, doub
       __syncthreads();
     }
     stamp();  // panel exchanged
-    // phase 3: trailing update, 4x4 register tiles on the transposed panels.  Work items: the lower-triangle tiles of A,
-    // then of G, dealt to the CTAs in contiguous runs (neighbouring lanes read neighbouring columns: no bank
-    // conflicts); then this CTA's own W tiles.
-    {
+    // phase 3.  CTA 0: the next diagonal block = leading 32 x 32 tile of the trailing update, formed from the panel
+    // straight into shared memory, then factorised.  CTAs 1..7: the rest of the trailing update, 4x4 register tiles on
+    // the transposed panels -- the lower-triangle tiles of A, then of G (rows >= 32 of the trailing matrix), dealt in
+    // contiguous runs (neighbouring lanes read neighbouring columns: no bank conflicts); then their own W tiles.
+    if (crank == 0) {
+      const int nb2 = min(NB, nr);
+      for (int e = tid; e < NB * LD; e += kTailThreads) {
+        const int i = e / LD, j = e % LD;
+        double va = 0.0, vg = 0.0;
+        if (i < nb2 && j <= i) {
+          double sa = 0.0, sg = 0.0;
+#pragma unroll 8
+          for (int c = 0; c < NB; ++c) {
+            sa += PT_A[(size_t)c * ldt + i] * PT_A[(size_t)c * ldt + j];
+            if (!full) sg += PT_G[(size_t)c * ldt + i] * PT_G[(size_t)c * ldt + j];
+          }
+          va = A[(size_t)(r0 + i) * ld + r0 + j] - sa;
+          if (!full) vg = G[(size_t)(r0 + i) * ld + r0 + j] - sg;
+        }
+        if (j == i && i < NB) { dgA[i] = (i < nb2) ? va : 1.0; dgG[i] = (i < nb2) ? vg : 1.0; va = 0.0; vg = 0.0; }
+        DA[e] = va;
+        DG[e] = vg;
+      }
+      factor_block(r0, nb2, false);
+    } else {
       const int nt = (nr + 3) / 4, ntile = nt * (nt + 1) / 2;
-      const int nitems = full ? ntile : 2 * ntile;
-      const int run = (nitems + C - 1) / C;
-      const int first = crank * run;
+      constexpr int kLead = (NB / 4) * (NB / 4 + 1) / 2;  // tiles of the leading 32 x 32 block: CTA 0's
+      const int nrest = max(0, ntile - kLead);
+      const int nitems = full ? nrest : 2 * nrest;
+      const int run = (nitems + C - 2) / (C - 1);
+      const int first = (crank - 1) * run;
       const int mine = max(0, min(run, nitems - first));
       const int nloc3 = mine + ncw4 * nt;
       for (int q = tid; q < nloc3; q += kTailThreads) {
         if (q < mine) {
           const int it = first + q;
-          const bool isG = it >= ntile;
+          const bool isG = it >= nrest;
           int ti, tj;
-          tc_tile_index(isG ? it - ntile : it, ti, tj);
+          tc_tile_index((isG ? it - nrest : it) + kLead, ti, tj);
           double* Mat = (isG ? G : A) + (size_t)r0 * ld + r0;
           const double* PT = isG ? PT_G : PT_A;
           double old[4][4];
@@ -392,9 +494,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(int n, int ld, doub
         }
       }
     }
-    stamp();  // trailing computed (CTA 0)
-    cluster.sync();
-    stamp();  // trailing done
+    stamp();  // next diagonal block done (CTA 0)
   }
   cluster.sync();
   if (gtid == 0) *rank_out = s_rankA;

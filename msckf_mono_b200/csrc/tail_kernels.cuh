@@ -8,21 +8,25 @@
 
 namespace mb {
 
-// One 32 x 32 output tile per CTA of 64 threads (4 x 4 register tile per thread), operands streamed through shared
-// memory in 32-deep k-slabs with the next slab prefetched into registers while the current one is multiplied:
-// at n <= 639 these products are bound by the L2 round trip per slab, not by the fp64 pipe, so small tiles
-// (many CTAs) and prefetching are what matters.  LA(k, a) / LB(k, b) fetch operand elements, EPI(a, b, acc) stores.
+// One 32 x 32 output tile per CTA of 128 threads: two halves of 64 threads (4 x 4 register tile per thread) split every
+// 32-deep k-slab between them (16 k each) and are summed once at the end through shared memory (fixed order:
+// deterministic).  Operands stream through shared memory with the next slab prefetched into registers while the
+// current one is multiplied: at n <= 639 these products are bound by the latency of a slab (L2 round trip + a chain of
+// FMAs issued by one warp per sub-partition), not by the fp64 pipe, so halving the chain per warp is what matters.
+// LA(k, a) / LB(k, b) fetch operand elements, EPI(a, b, acc) stores.
+constexpr int kGemmThreads = 128;
 template <class LoadA, class LoadB, class Epi>
 __device__ __forceinline__ void gemm_tile32(int n, int k_begin, int a0, int b0, LoadA LA, LoadB LB, Epi EPI) {
   __shared__ __align__(16) double sA[32][32], sB[32][32];
-  const int tid = threadIdx.x;       // 64 threads
-  const int tx = tid & 7, ty = tid >> 3;
+  const int tid = threadIdx.x;       // 128 threads
+  const int half = tid >> 6, t = tid & 63;
+  const int tx = t & 7, ty = t >> 3;
   double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-  double pa[16], pb[16];
+  double pa[8], pb[8];
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int e = tid + 64 * u, kk = e >> 5, cc = e & 31;
+    for (int u = 0; u < 8; ++u) {
+      const int e = tid + kGemmThreads * u, kk = e >> 5, cc = e & 31;
       const int k = k0 + kk;
       pa[u] = (k < n && a0 + cc < n) ? LA(k, a0 + cc) : 0.0;
       pb[u] = (k < n && b0 + cc < n) ? LB(k, b0 + cc) : 0.0;
@@ -32,36 +36,48 @@ __device__ __forceinline__ void gemm_tile32(int n, int k_begin, int a0, int b0, 
   for (int k0 = k_begin; k0 < n; k0 += 32) {
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int e = tid + 64 * u, kk = e >> 5, cc = e & 31;
+    for (int u = 0; u < 8; ++u) {
+      const int e = tid + kGemmThreads * u, kk = e >> 5, cc = e & 31;
       sA[kk][cc] = pa[u];
       sB[kk][cc] = pb[u];
     }
     __syncthreads();
     if (k0 + 32 < n) fetch(k0 + 32);
 #pragma unroll 8
-    for (int kk = 0; kk < 32; ++kk) {
+    for (int q = 0; q < 16; ++q) {
+      const int kk = 16 * half + q;
       const double2 a01 = *reinterpret_cast<const double2*>(&sA[kk][4 * ty]), a23 = *reinterpret_cast<const double2*>(&sA[kk][4 * ty + 2]);
       const double2 b01 = *reinterpret_cast<const double2*>(&sB[kk][4 * tx]), b23 = *reinterpret_cast<const double2*>(&sB[kk][4 * tx + 2]);
       const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
       for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[p][q] += a[p] * b[q];
+        for (int qq = 0; qq < 4; ++qq) acc[p][qq] += a[p] * b[qq];
     }
   }
+  __syncthreads();
+  double* red = &sA[0][0];  // [16][64]
+  if (half == 1) {
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int a = a0 + 4 * ty + p, b = b0 + 4 * tx + q;
-      if (a < n && b < n) EPI(a, b, acc[p][q]);
-    }
+      for (int q = 0; q < 4; ++q) red[(4 * p + q) * 64 + t] = acc[p][q];
+  }
+  __syncthreads();
+  if (half == 0) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int a = a0 + 4 * ty + p, b = b0 + 4 * tx + q;
+        if (a < n && b < n) EPI(a, b, acc[p][q] + red[(4 * p + q) * 64 + t]);
+      }
+  }
 }
 
 // TP[a][b] = sum_k T2[a][k] * P[k][b]      (T2 columns < 15 are zero)
 template <class S>
-__global__ void __launch_bounds__(64) k_gemm_tp(int n, int ld, const double* __restrict__ T2, const S* __restrict__ P, int ldp,
+__global__ void __launch_bounds__(kGemmThreads) k_gemm_tp(int n, int ld, const double* __restrict__ T2, const S* __restrict__ P, int ldp,
                                                double* __restrict__ TP) {
   gemm_tile32(n, kImuDim, blockIdx.y * 32, blockIdx.x * 32,
               [&](int k, int a) { return T2[(size_t)a * ld + k]; },
@@ -70,7 +86,7 @@ __global__ void __launch_bounds__(64) k_gemm_tp(int n, int ld, const double* __r
 }
 
 // S2[a][b] = sum_k TP[a][k] * T2[b][k] + R2[a][b]
-__global__ void __launch_bounds__(64) k_gemm_s(int n, int ld, const double* __restrict__ TP, const double* __restrict__ T2,
+__global__ void __launch_bounds__(kGemmThreads) k_gemm_s(int n, int ld, const double* __restrict__ TP, const double* __restrict__ T2,
                                               const double* __restrict__ R2, double* __restrict__ S2) {
   gemm_tile32(n, kImuDim, blockIdx.y * 32, blockIdx.x * 32,  // T2 columns < 15 are zero
               [&](int k, int a) { return TP[(size_t)a * ld + k]; },
@@ -80,7 +96,7 @@ __global__ void __launch_bounds__(64) k_gemm_s(int n, int ld, const double* __re
 
 // P <- P - W^T W (lower-triangular tile pairs; written in the filter precision, exactly symmetric by construction)
 template <class S>
-__global__ void __launch_bounds__(64) k_syrk(int n, int ld, const double* __restrict__ Wm, S* __restrict__ P, int ldp,
+__global__ void __launch_bounds__(kGemmThreads) k_syrk(int n, int ld, const double* __restrict__ Wm, S* __restrict__ P, int ldp,
                                             const int* __restrict__ m_in) {
   if (*m_in == 0) return;
   int pidx = blockIdx.x, ta = 0;

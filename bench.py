@@ -319,7 +319,7 @@ def main():
             sj.append(int(x))
         dd = [int(x) for x in list(buf)[64:80]]
         if dd[0]:
-            print("tail diag-block fine stamps, A factor, pivots 20 and 21 (ns since pivot start: dot, shfl, decide, rsqrt+stores, publish):",
+            print("tail diag-block fine stamps, A factor, pivots 20 and 21 (ns since pivot start: shuffles + FMA, decide, next bracket + rsqrt, stores, publish):",
                   [[dd[6 * q + u] - dd[6 * q] for u in range(1, 6)] for q in range(2)], "pivot-to-pivot:", dd[6] - dd[0],
                   "| block 0: loaded -> workers done (us):", round((dd[13] - dd[12]) / 1e3, 2), file=sys.stderr)
         print("jac stamps (us since start):", [round((x - sj[0]) / 1e3, 1) for x in sj], file=sys.stderr)

@@ -1,14 +1,16 @@
 // msckf_mono_b200/csrc/tail_cluster.cuh
-// The serial part of the EKF tail as ONE thread-block-cluster kernel (8 CTAs on 8 SMs of one GPC):
+// The serial part of the EKF tail for LARGE windows (15 + 6M > ~220: the fused form of tail_fused.cuh does not fit the
+// shared memory of a CTA any more) as ONE thread-block-cluster kernel (8 CTAs on 8 SMs of one GPC):
 //     Gamma (Gram matrix of the basis)      -> rank decision        }  rank-revealing Cholesky of Gamma and S''
 //     S'' = L L^T over the kept indices                              }  in lockstep, blocked by NB
-//     W = L^-1 [T''P | r'']                                         (forward substitution, RHS columns sharded)
+//     W = L^-1 [T''P | r'']                                         (forward substitution as a second sweep, RHS columns
+//                                                                    sharded over the cluster)
 // followed by  P <- P - W^T W (k_syrk, all SMs) and dx = W^T y + state injection (k_inject)   (msckf.h:1373-1418)
 // The matrices stay in global memory (they are L2 resident: n <= 639, fp64); cluster barriers (release/acquire
-// at cluster scope, ~0.3 us) order the phases, so the O(n^3) trailing updates, the substitutions and the SYRK
-// are spread over the cluster's SMs while the O(n NB^2) diagonal-block factorisations run on CTA 0.
-// Inner loops are register tiled (4x4 outputs per thread, operands read as contiguous vectors from a transposed
-// panel in shared memory): the fp64 FMA pipe, not the shared-memory port, is the limit.
+// at cluster scope) order the phases.  Diagonal blocks: one warp of CTA 0; panel rows: solved redundantly by every CTA
+// (one thread per row) into a transposed shared panel; trailing update: 4x4 register tiles dealt to the CTAs.
+// This is the first-generation design; tail_fused.cuh documents what was measured on it and changed for the default
+// path.  Also shared with tail_fused.cuh: the tile helpers below and k_inject.
 #pragma once
 #include <cooperative_groups.h>
 #include "common.cuh"

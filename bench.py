@@ -266,7 +266,8 @@ def main():
             e2e_times.append(dt)
     assert np.isfinite(st["p_I_G"]).all()
     e2e_s = float(np.sum(e2e_times))
-    rep_bytes = 4 * 4 * N_FEAT + 4 * 3 * N_FEAT + 4 * N_FEAT + 8
+    up16 = lambda x: (x + 15) & ~15  # the engine's packed report block: (m, rank) | 5 int flags per track | p_f_G | gamma, one D2H copy
+    rep_bytes = 16 + 5 * up16(4 * N_FEAT) + up16(4 * 3 * N_FEAT) + up16(4 * N_FEAT)
     state_bytes = 1192 + 8 * 4 * N_CLONES  # sizeof(DevState<float>) + clone poses
     # ---------------------------------------------------------------- batched side measurement (multi-stream pipelining)
     B = args.batch

@@ -85,8 +85,37 @@ struct Engine : EngineBase {
          *d_bb = nullptr, *d_T2 = nullptr, *d_R2 = nullptr, *d_r2 = nullptr, *d_TP = nullptr, *d_S2 = nullptr, *d_W = nullptr, *d_G = nullptr,
          *d_y = nullptr, *d_dx = nullptr, *d_idiag = nullptr;
   // pinned host
-  int *h_off = nullptr, *h_idx = nullptr, *h_flags = nullptr /*cm,tri,valid,accept: 4*Tmax*/, *h_mr = nullptr /*m, rank*/;
+  // One packed input block and one packed report block per update (a single H2D and a single D2H copy): the typed
+  // pointers below (d_off .. d_pfg_given, d_cmeff .. d_gamma and their host mirrors) are carved out of them by layout(),
+  // tightly for the batch at hand -- deterministic in (N, O), which the CUDA-graph key contains.
+  unsigned char *d_in = nullptr, *h_in = nullptr, *d_rep = nullptr, *h_rep = nullptr;
+  size_t in_bytes = 0, rep_bytes = 0;
+  int *h_off = nullptr, *h_idx = nullptr, *h_cmeff = nullptr, *h_cm = nullptr, *h_tri = nullptr, *h_valid = nullptr, *h_accept = nullptr,
+      *h_mr = nullptr /*m, rank*/;
   S *h_obs = nullptr, *h_pfg_in = nullptr, *h_pfg = nullptr, *h_gamma = nullptr;
+  static size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
+  void layout(int N, int O) {
+    size_t o = 0;
+    auto take = [&](unsigned char* dbase, unsigned char* hbase, size_t bytes, void** dp, void** hp) {
+      *dp = dbase + o; *hp = hbase + o; o += up16(bytes);
+    };
+    take(d_in, h_in, sizeof(int) * (N + 1), (void**)&d_off, (void**)&h_off);
+    take(d_in, h_in, sizeof(int) * (size_t)O, (void**)&d_idx, (void**)&h_idx);
+    take(d_in, h_in, sizeof(S) * 2 * (size_t)O, (void**)&d_obs, (void**)&h_obs);
+    take(d_in, h_in, sizeof(S) * 3 * (size_t)N, (void**)&d_pfg_given, (void**)&h_pfg_in);
+    in_bytes = o;
+    o = 0;
+    take(d_rep, h_rep, sizeof(int) * 2, (void**)&d_m, (void**)&h_mr);
+    d_rank = d_m + 1;
+    take(d_rep, h_rep, sizeof(int) * (size_t)N, (void**)&d_cmeff, (void**)&h_cmeff);
+    take(d_rep, h_rep, sizeof(int) * (size_t)N, (void**)&d_cm, (void**)&h_cm);
+    take(d_rep, h_rep, sizeof(int) * (size_t)N, (void**)&d_tri, (void**)&h_tri);
+    take(d_rep, h_rep, sizeof(int) * (size_t)N, (void**)&d_valid, (void**)&h_valid);
+    take(d_rep, h_rep, sizeof(int) * (size_t)N, (void**)&d_accept, (void**)&h_accept);
+    take(d_rep, h_rep, sizeof(S) * 3 * (size_t)N, (void**)&d_pfg, (void**)&h_pfg);
+    take(d_rep, h_rep, sizeof(S) * (size_t)N, (void**)&d_gamma, (void**)&h_gamma);
+    rep_bytes = o;
+  }
   mb::DevState<S>* h_st = nullptr;
   int nmax = 0, ldp = 0, ld = 0;
   int pending_n = 0, pending_mode = -1;
@@ -137,24 +166,23 @@ struct Engine : EngineBase {
     CK(cudaMemsetAsync(d_poses, 0, sizeof(S) * mb::kPoseStride * (size_t)(Mmax + 1), stream));
     CK(cudaMemsetAsync(d_poses2, 0, sizeof(S) * mb::kPoseStride * (size_t)(Mmax + 1), stream));
     const size_t T = Tmax, O = Omax;
-    CK(cudaMalloc(&d_off, sizeof(int) * (T + 1)));
-    CK(cudaMalloc(&d_idx, sizeof(int) * O));
-    for (int** p : {&d_cm, &d_tri, &d_valid, &d_src, &d_accept, &d_rows, &d_scratch}) CK(cudaMalloc(p, sizeof(int) * T));
+    for (int** p : {&d_src, &d_rows, &d_scratch}) CK(cudaMalloc(p, sizeof(int) * T));
+    {
+      const size_t cap_in = up16(sizeof(int) * (T + 1)) + up16(sizeof(int) * O) + up16(sizeof(S) * 2 * O) + up16(sizeof(S) * 3 * T);
+      const size_t cap_rep = up16(sizeof(int) * 2) + 5 * up16(sizeof(int) * T) + up16(sizeof(S) * 3 * T) + up16(sizeof(S) * T);
+      CK(cudaMalloc(&d_in, cap_in)); CK(cudaMallocHost(&h_in, cap_in));
+      CK(cudaMalloc(&d_rep, cap_rep)); CK(cudaMallocHost(&h_rep, cap_rep));
+      CK(cudaMemsetAsync(d_rep, 0, cap_rep, stream));
+      layout((int)T, (int)O);
+    }
     CK(cudaMalloc(&d_rowoff, sizeof(int) * (T + 1)));
-    CK(cudaMalloc(&d_cmeff, sizeof(int) * T));
     CK(cudaMalloc(&d_csnap, sizeof(unsigned long long)));
     CK(cudaMalloc(&d_prof, sizeof(unsigned long long) * 80));
     CK(cudaMalloc(&d_done, sizeof(unsigned)));
     CK(cudaMemsetAsync(d_done, 0, sizeof(unsigned), stream));
     CK(cudaMemsetAsync(d_prof, 0, sizeof(unsigned long long) * 80, stream));
     CK(cudaMalloc(&d_keep, sizeof(int) * nmax));
-    CK(cudaMalloc(&d_m, sizeof(int) * 2));
-    d_rank = d_m + 1;
     CK(cudaMalloc(&d_keepclones, sizeof(int) * (Mmax + 1)));
-    CK(cudaMalloc(&d_obs, sizeof(S) * 2 * O));
-    CK(cudaMalloc(&d_pfg, sizeof(S) * 3 * T));
-    CK(cudaMalloc(&d_pfg_given, sizeof(S) * 3 * T));
-    CK(cudaMalloc(&d_gamma, sizeof(S) * T));
     CK(cudaMalloc(&d_Xg, sizeof(S) * 12 * O));
     CK(cudaMalloc(&d_rg, sizeof(S) * 2 * O));
     CK(cudaMalloc(&d_Vg, sizeof(S) * 6 * O));
@@ -173,14 +201,6 @@ struct Engine : EngineBase {
     CK(cudaMalloc(&d_y, sizeof(double) * nmax));
     CK(cudaMalloc(&d_dx, sizeof(double) * nmax));
     CK(cudaMemsetAsync(d_dx, 0, sizeof(double) * nmax, stream));
-    CK(cudaMallocHost(&h_off, sizeof(int) * (T + 1)));
-    CK(cudaMallocHost(&h_idx, sizeof(int) * O));
-    CK(cudaMallocHost(&h_flags, sizeof(int) * 4 * T));
-    CK(cudaMallocHost(&h_mr, sizeof(int) * 2));
-    CK(cudaMallocHost(&h_obs, sizeof(S) * 2 * O));
-    CK(cudaMallocHost(&h_pfg_in, sizeof(S) * 3 * T));
-    CK(cudaMallocHost(&h_pfg, sizeof(S) * 3 * T));
-    CK(cudaMallocHost(&h_gamma, sizeof(S) * T));
     CK(cudaMallocHost(&h_st, sizeof(mb::DevState<S>)));
     // opt in to large dynamic shared memory
     CK(cudaFuncSetAttribute(mb::k_tri<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
@@ -195,11 +215,11 @@ struct Engine : EngineBase {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     if (g_exec) cudaGraphExecDestroy(g_exec);
-    void* dv[] = {d_st, d_P, d_P2, d_poses, d_poses2, d_off, d_idx, d_cm, d_tri, d_valid, d_src, d_accept, d_rows, d_rowoff,
-                  d_scratch, d_keep, d_m, d_keepclones, d_cmeff, d_csnap, d_prof, d_done, d_obs, d_pfg, d_pfg_given, d_gamma, d_Xg, d_rg, d_Vg, d_taug, d_Z, d_Yq,
+    void* dv[] = {d_st, d_P, d_P2, d_poses, d_poses2, d_in, d_rep, d_src, d_rows, d_rowoff,
+                  d_scratch, d_keep, d_keepclones, d_csnap, d_prof, d_done, d_Xg, d_rg, d_Vg, d_taug, d_Z, d_Yq,
                   d_ur, d_G1p, d_G2p, d_D1, d_D2, d_bb, d_T2, d_R2, d_TP, d_S2, d_W, d_G, d_r2, d_y, d_dx, d_idiag};
     for (void* p : dv) if (p) cudaFree(p);
-    void* hv[] = {h_off, h_idx, h_flags, h_mr, h_obs, h_pfg_in, h_pfg, h_gamma, h_st};
+    void* hv[] = {h_in, h_rep, h_st};
     for (void* p : hv) if (p) cudaFreeHost(p);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -288,17 +308,13 @@ struct Engine : EngineBase {
     }
     for (int o = 0; o < O; ++o)
       if (tr->clone_index[o] < 0 || tr->clone_index[o] >= M) return fail(MSCKF_B200_ERR_ARG, "clone_index out of range");
+    if (mode == MSCKF_B200_RESIDUALIZE && !tr->p_f_G) return fail(MSCKF_B200_ERR_ARG, "RESIDUALIZE needs p_f_G");
+    layout(N, O);
     memcpy(h_off, tr->obs_offset, sizeof(int) * (N + 1));
     memcpy(h_idx, tr->clone_index, sizeof(int) * O);
     memcpy(h_obs, tr->obs, sizeof(S) * 2 * (size_t)O);
-    CK(cudaMemcpyAsync(d_off, h_off, sizeof(int) * (N + 1), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(d_idx, h_idx, sizeof(int) * O, cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(d_obs, h_obs, sizeof(S) * 2 * (size_t)O, cudaMemcpyHostToDevice, stream));
-    if (mode == MSCKF_B200_RESIDUALIZE) {
-      if (!tr->p_f_G) return fail(MSCKF_B200_ERR_ARG, "RESIDUALIZE needs p_f_G");
-      memcpy(h_pfg_in, tr->p_f_G, sizeof(S) * 3 * (size_t)N);
-      CK(cudaMemcpyAsync(d_pfg_given, h_pfg_in, sizeof(S) * 3 * (size_t)N, cudaMemcpyHostToDevice, stream));
-    }
+    if (mode == MSCKF_B200_RESIDUALIZE) memcpy(h_pfg_in, tr->p_f_G, sizeof(S) * 3 * (size_t)N);
+    CK(cudaMemcpyAsync(d_in, h_in, mode == MSCKF_B200_RESIDUALIZE ? in_bytes : (size_t)((unsigned char*)d_pfg_given - d_in), cudaMemcpyHostToDevice, stream));
     st_O = O; st_Lmax = Lmax;
     staged = true;
     return 0;
@@ -448,18 +464,9 @@ struct Engine : EngineBase {
 
   int queue_report(int N, int mode) {
     if (timed_region) CK(cudaEventRecord(ev_t1, stream));
-    // report back (pinned), still asynchronous
-    if (mode != MSCKF_B200_RESIDUALIZE) {
-      CK(cudaMemcpyAsync(h_flags, mode == MSCKF_B200_MARGINALIZE ? d_cmeff : d_cm, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
-      CK(cudaMemcpyAsync(h_flags + Tmax, d_tri, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
-      CK(cudaMemcpyAsync(h_pfg, d_pfg, sizeof(S) * 3 * (size_t)N, cudaMemcpyDeviceToHost, stream));
-    }
-    if (mode != MSCKF_B200_TRIANGULATE) {
-      CK(cudaMemcpyAsync(h_flags + 2 * (size_t)Tmax, d_valid, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
-      CK(cudaMemcpyAsync(h_flags + 3 * (size_t)Tmax, d_accept, sizeof(int) * N, cudaMemcpyDeviceToHost, stream));
-      CK(cudaMemcpyAsync(h_gamma, d_gamma, sizeof(S) * N, cudaMemcpyDeviceToHost, stream));
-      CK(cudaMemcpyAsync(h_mr, d_m, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream));
-    }
+    // report back (pinned), still asynchronous: one copy of the packed block
+    (void)mode;
+    if (N > 0) CK(cudaMemcpyAsync(h_rep, d_rep, rep_bytes, cudaMemcpyDeviceToHost, stream));
     return 0;
   }
 
@@ -473,13 +480,13 @@ struct Engine : EngineBase {
     rep->m = 0; rep->rank = 0;
     if (N == 0) return 0;
     if (mode != MSCKF_B200_RESIDUALIZE) {
-      if (rep->cm_ok) memcpy(rep->cm_ok, h_flags, sizeof(int) * N);
-      if (rep->tri_ok) memcpy(rep->tri_ok, h_flags + Tmax, sizeof(int) * N);
+      if (rep->cm_ok) memcpy(rep->cm_ok, mode == MSCKF_B200_MARGINALIZE ? h_cmeff : h_cm, sizeof(int) * N);
+      if (rep->tri_ok) memcpy(rep->tri_ok, h_tri, sizeof(int) * N);
       if (rep->p_f_G) memcpy(rep->p_f_G, h_pfg, sizeof(S) * 3 * (size_t)N);
     }
     if (mode != MSCKF_B200_TRIANGULATE) {
-      if (rep->valid) memcpy(rep->valid, h_flags + 2 * (size_t)Tmax, sizeof(int) * N);
-      if (rep->accepted) memcpy(rep->accepted, h_flags + 3 * (size_t)Tmax, sizeof(int) * N);
+      if (rep->valid) memcpy(rep->valid, h_valid, sizeof(int) * N);
+      if (rep->accepted) memcpy(rep->accepted, h_accept, sizeof(int) * N);
       if (rep->gamma) memcpy(rep->gamma, h_gamma, sizeof(S) * N);
       rep->m = h_mr[0];
       rep->rank = h_mr[1];
@@ -508,9 +515,14 @@ struct Engine : EngineBase {
 
   int get_state(void* imu_, void* poses_) override {
     CK(cudaSetDevice(device));
+    std::vector<S> tmp;
+    if (imu_) CK(cudaMemcpyAsync(h_st, d_st, sizeof(mb::DevState<S>), cudaMemcpyDeviceToHost, stream));
+    if (poses_ && M > 0) {
+      tmp.resize((size_t)mb::kPoseStride * M);
+      CK(cudaMemcpyAsync(tmp.data(), d_poses, sizeof(S) * tmp.size(), cudaMemcpyDeviceToHost, stream));
+    }
+    CK(cudaStreamSynchronize(stream));  // one synchronisation for both copies
     if (imu_) {
-      CK(cudaMemcpyAsync(h_st, d_st, sizeof(mb::DevState<S>), cudaMemcpyDeviceToHost, stream));
-      CK(cudaStreamSynchronize(stream));
       S* o = (S*)imu_;
       const mb::DevState<S>& s = *h_st;
       for (int i = 0; i < 3; ++i) {
@@ -520,9 +532,6 @@ struct Engine : EngineBase {
       for (int i = 0; i < 4; ++i) { o[15 + i] = s.q_IG[i]; o[25 + i] = s.q_IG_null[i]; }
     }
     if (poses_ && M > 0) {
-      std::vector<S> tmp((size_t)mb::kPoseStride * M);
-      CK(cudaMemcpyAsync(tmp.data(), d_poses, sizeof(S) * tmp.size(), cudaMemcpyDeviceToHost, stream));
-      CK(cudaStreamSynchronize(stream));
       S* o = (S*)poses_;
       for (int k = 0; k < M; ++k) {
         const S* p = tmp.data() + mb::kPoseStride * k;

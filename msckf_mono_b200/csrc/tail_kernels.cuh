@@ -8,24 +8,27 @@
 
 namespace mb {
 
-// One 32 x 32 output tile per CTA of 128 threads: two halves of 64 threads (4 x 4 register tile per thread) split every
-// 32-deep k-slab between them (16 k each) and are summed once at the end through shared memory (fixed order:
+// One 32 x 32 output tile per CTA of 256 threads: four groups of 64 threads (4 x 4 register tile per thread) split every
+// 32-deep k-slab between them (8 k each) and are summed once at the end through shared memory (fixed order:
 // deterministic).  Operands stream through shared memory with the next slab prefetched into registers while the
 // current one is multiplied: at n <= 639 these products are bound by the latency of a slab (L2 round trip + a chain of
-// FMAs issued by one warp per sub-partition), not by the fp64 pipe, so halving the chain per warp is what matters.
+// FMAs issued by one warp per sub-partition), not by the fp64 pipe, so shortening the chain per warp is what matters
+// (measured at config B: 27 us with 64 threads, 18 us with 128, see profiles/).
 // LA(k, a) / LB(k, b) fetch operand elements, EPI(a, b, acc) stores.
-constexpr int kGemmThreads = 128;
+constexpr int kGemmThreads = 256;
 template <class LoadA, class LoadB, class Epi>
 __device__ __forceinline__ void gemm_tile32(int n, int k_begin, int a0, int b0, LoadA LA, LoadB LB, Epi EPI) {
+  constexpr int kParts = kGemmThreads / 64, kPer = 32 / kParts, kFetch = 1024 / kGemmThreads;
   __shared__ __align__(16) double sA[32][32], sB[32][32];
-  const int tid = threadIdx.x;       // 128 threads
-  const int half = tid >> 6, t = tid & 63;
+  __shared__ double red[kParts - 1][16][64];
+  const int tid = threadIdx.x;
+  const int part = tid >> 6, t = tid & 63;
   const int tx = t & 7, ty = t >> 3;
   double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-  double pa[8], pb[8];
+  double pa[kFetch], pb[kFetch];
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < kFetch; ++u) {
       const int e = tid + kGemmThreads * u, kk = e >> 5, cc = e & 31;
       const int k = k0 + kk;
       pa[u] = (k < n && a0 + cc < n) ? LA(k, a0 + cc) : 0.0;
@@ -36,16 +39,16 @@ __device__ __forceinline__ void gemm_tile32(int n, int k_begin, int a0, int b0, 
   for (int k0 = k_begin; k0 < n; k0 += 32) {
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < kFetch; ++u) {
       const int e = tid + kGemmThreads * u, kk = e >> 5, cc = e & 31;
       sA[kk][cc] = pa[u];
       sB[kk][cc] = pb[u];
     }
     __syncthreads();
     if (k0 + 32 < n) fetch(k0 + 32);
-#pragma unroll 8
-    for (int q = 0; q < 16; ++q) {
-      const int kk = 16 * half + q;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int kk = kPer * part + q;
       const double2 a01 = *reinterpret_cast<const double2*>(&sA[kk][4 * ty]), a23 = *reinterpret_cast<const double2*>(&sA[kk][4 * ty + 2]);
       const double2 b01 = *reinterpret_cast<const double2*>(&sB[kk][4 * tx]), b23 = *reinterpret_cast<const double2*>(&sB[kk][4 * tx + 2]);
       const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
@@ -55,22 +58,23 @@ __device__ __forceinline__ void gemm_tile32(int n, int k_begin, int a0, int b0, 
         for (int qq = 0; qq < 4; ++qq) acc[p][qq] += a[p] * b[qq];
     }
   }
-  __syncthreads();
-  double* red = &sA[0][0];  // [16][64]
-  if (half == 1) {
+  if (part > 0) {
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) red[(4 * p + q) * 64 + t] = acc[p][q];
+      for (int q = 0; q < 4; ++q) red[part - 1][4 * p + q][t] = acc[p][q];
   }
   __syncthreads();
-  if (half == 0) {
+  if (part == 0) {
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int a = a0 + 4 * ty + p, b = b0 + 4 * tx + q;
-        if (a < n && b < n) EPI(a, b, acc[p][q] + red[(4 * p + q) * 64 + t]);
+        double v = acc[p][q];
+#pragma unroll
+        for (int r = 0; r < kParts - 1; ++r) v += red[r][4 * p + q][t];
+        if (a < n && b < n) EPI(a, b, v);
       }
   }
 }

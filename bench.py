@@ -298,6 +298,18 @@ def main():
             f.marginalizeCollect()
         if r >= 1:
             batched2_s.append(time.perf_counter() - t0)
+    # the same 32 filters' worth of work through the batched C entry point (host work on several threads)
+    from msckf_mono_b200.cview import marginalize_batch
+    host_threads = max(1, min(8, (os.cpu_count() or 1)))
+    b3filts = [ready_filter(DTYPE, seq=13000 + rank * 1000 + i, device=local_rank) for i in range(B2 * 2)]
+    batched3_s = []
+    for r in range(2):
+        grp = b3filts[r * B2:(r + 1) * B2]
+        flush_l2()
+        t0 = time.perf_counter()
+        marginalize_batch(grp, threads=host_threads)
+        if r >= 1:
+            batched3_s.append(time.perf_counter() - t0)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     # ---------------------------------------------------------------- per-kernel profile (CUDA events between kernels)
@@ -329,7 +341,8 @@ def main():
     dom = max(kern_ms, key=kern_ms.get)
 
     # ---------------------------------------------------------------- reduce over ranks
-    dev_ms, e2e_s, bsum, b2sum = shard.max_over_ranks([dev_ms, e2e_s, float(np.sum(batched_s)), float(np.sum(batched2_s))], device="cuda")
+    dev_ms, e2e_s, bsum, b2sum, b3sum = shard.max_over_ranks(
+        [dev_ms, e2e_s, float(np.sum(batched_s)), float(np.sum(batched2_s)), float(np.sum(batched3_s))], device="cuda")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -370,14 +383,16 @@ def main():
                      "kernel": dom, "kernel_ms": kern_ms[dom], "peak_source": peak_src, "algorithmic_bytes_per_update": bytes_alg,
                      "whole_update_gbs": bytes_alg / (dev_ms / K * 1e-3) / 1e9,
                      "reference_path_gflop_per_update": algorithmic_flops(N_FEAT, N_CLONES) / 1e9,
-                     "note": "the update is latency-bound (14 short dependent kernels); see DESIGN.md for the per-kernel table",
+                     "note": "the update is latency-bound (11 short dependent kernels); see DESIGN.md for the per-kernel table",
                      "kernel_ms_all": kern_ms},
         "cpu_baseline": {"value": cpu_val, "unit": "updates/s", "cores": 1, "kind": "port",
                          "sample": f"{cpu_n} marginalize() calls of the same {N_FEAT}x{N_CLONES} fp32 workload in {cpu_wall:.1f} s, "
                                    "oracle/ (CPU restatement of the reference's Eigen path, thin-Q form), single thread like the reference"},
         "batched": {"filters_per_gpu_in_flight": B, "value": world * B * len(batched_s) / bsum, "unit": "updates/s",
                     "path": "marginalizeLaunch() on all filters, then marginalizeCollect() (one stream per filter), host wall clock incl. copies",
-                    "value_32_in_flight": world * B2 * len(batched2_s) / b2sum},
+                    "value_32_in_flight": world * B2 * len(batched2_s) / b2sum,
+                    "value_32_batch_api": world * B2 * len(batched3_s) / b3sum, "batch_api_host_threads": host_threads,
+                    "batch_api": "msckf_mono_marginalize_batch (C view) = msckf_b200_update_batch semantics: launch all, collect all, host work on threads"},
         "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line))

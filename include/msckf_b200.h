@@ -96,6 +96,12 @@ int msckf_b200_kernel_times(msckf_b200_engine* e, float* ms, const char** names,
 int msckf_b200_tail_profile(msckf_b200_engine* e, unsigned long long* out, int cap);
 /* update_async + fetch */
 int msckf_b200_update(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks, msckf_b200_report* report);
+/* Batched variant for independent filters (sequences / Monte-Carlo trials sharing one GPU): update_async on
+ * every engine, then fetch on every engine, the per-filter host work (validation, packing, launch, report) spread over
+ * `threads` host threads.  Every filter runs on its own stream, so their kernels overlap on the device.  Results are
+ * identical to n separate msckf_b200_update calls.  reports may be NULL.  Returns the first non-zero status. */
+int msckf_b200_update_batch(msckf_b200_engine** engines, int n, int mode, const msckf_b200_tracks* tracks, msckf_b200_report* reports,
+                            int threads);
 /* covariance / pose gather of pruneEmptyStates msckf.h:685-761 and pruneRedundantStates :616-681:
  * keep[] = ascending positional indices of the clones that survive */
 int msckf_b200_prune(msckf_b200_engine* e, const int* keep, int n_keep);

@@ -47,6 +47,9 @@ int msckf_mono_pack_queued(void* h, int* obs_offset, double* obs, int* clone_ind
 /* pipelining helpers: marginalize() = launch + collect */
 int msckf_mono_marginalize_launch(void* h);
 int msckf_mono_marginalize_collect(void* h);
+/* marginalize() on n independent filters: launch on all, then collect on all, the host work of the filters spread over
+ * `threads` host threads (each filter has its own stream: the updates overlap on the GPU) */
+int msckf_mono_marginalize_batch(void** handles, int n, int threads);
 /* the msckf_b200_engine* beneath (for CUDA-event timing on its stream, launch counts, state copies) */
 void* msckf_mono_engine(void* h);
 /* copy the complete filter (host bookkeeping + device state) of src into dst; both must be initialised alike */

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/msckf_b200.h"
@@ -673,6 +674,31 @@ int msckf_b200_update(msckf_b200_engine* e, int mode, const msckf_b200_tracks* t
   int rc = e->impl->update_async(mode, tracks);
   if (rc != 0) { e->impl->fetch(nullptr); return rc; }
   return e->impl->fetch(report);
+}
+int msckf_b200_update_batch(msckf_b200_engine** engines, int n, int mode, const msckf_b200_tracks* tracks, msckf_b200_report* reports,
+                            int threads) {
+  if (n <= 0) return 0;
+  if (!engines || !tracks) return fail(MSCKF_B200_ERR_ARG, "null argument");
+  const int T = std::max(1, std::min(threads, n));
+  std::vector<int> rc(T, 0);
+  std::vector<std::string> err(T);
+  auto work = [&](int w) {
+    for (int i = w; i < n; i += T) {
+      const int r = engines[i]->impl->update_async(mode, &tracks[i]);
+      if (r != 0 && rc[w] == 0) { rc[w] = r; err[w] = g_err; }
+    }
+    for (int i = w; i < n; i += T) {
+      const int r = engines[i]->impl->fetch(reports ? &reports[i] : nullptr);
+      if (r != 0 && rc[w] == 0) { rc[w] = r; err[w] = g_err; }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
+  work(0);
+  for (auto& t : pool) t.join();
+  for (int w = 0; w < T; ++w)
+    if (rc[w] != 0) return fail(rc[w], err[w]);
+  return 0;
 }
 int msckf_b200_prune(msckf_b200_engine* e, const int* keep, int n_keep) { return e->impl->prune(keep, n_keep); }
 int msckf_b200_num_clones(msckf_b200_engine* e) { return e->impl->M; }

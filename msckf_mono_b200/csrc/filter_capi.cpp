@@ -1,7 +1,11 @@
 // msckf_mono_b200/csrc/filter_capi.cpp -- C view (include/msckf_mono_c.h) of the drop-in class
 // msckf_mono::MSCKF<float|double> (include/msckf_mono/msckf.h).  Host code only; links against the engine C-ABI.
 #include <cstring>
+#include <algorithm>
+#include <stdexcept>
 #include <string>
+#include <thread>
+#include <vector>
 #include <msckf_mono/msckf.h>
 #include <msckf_mono_c.h>
 
@@ -204,6 +208,25 @@ int msckf_mono_add_features(void* h, const double* z, const uint64_t* ids, int n
 int msckf_mono_marginalize(void* h) { return guard([&] { H->marginalize(); return 0; }); }
 int msckf_mono_marginalize_launch(void* h) { return guard([&] { H->marginalize_launch(); return 0; }); }
 int msckf_mono_marginalize_collect(void* h) { return guard([&] { H->marginalize_collect(); return 0; }); }
+int msckf_mono_marginalize_batch(void** handles, int n, int threads) {
+  return guard([&] {
+    if (n <= 0) return 0;
+    const int T = std::max(1, std::min(threads, n));
+    std::vector<std::string> err(T);
+    auto work = [&](int w) {
+      try {
+        for (int i = w; i < n; i += T) static_cast<Base*>(handles[i])->marginalize_launch();
+        for (int i = w; i < n; i += T) static_cast<Base*>(handles[i])->marginalize_collect();
+      } catch (const std::exception& e) { err[w] = e.what(); if (err[w].empty()) err[w] = "error"; }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
+    work(0);
+    for (auto& t : pool) t.join();
+    for (const auto& e : err) if (!e.empty()) throw std::runtime_error(e);
+    return 0;
+  });
+}
 int msckf_mono_prune_redundant_states(void* h) { return guard([&] { H->prune_redundant(); return 0; }); }
 int msckf_mono_prune_empty_states(void* h) { return guard([&] { H->prune_empty(); return 0; }); }
 int msckf_mono_finish(void* h) { return guard([&] { H->finish(); return 0; }); }

@@ -40,6 +40,16 @@ def pack_imu_state(s):
     return np.concatenate([np.asarray(s[k], float) for k in ("p_I_G", "v_I_G", "b_g", "b_a", "g", "q_IG")])
 
 
+def marginalize_batch(filters, threads=8):
+    """marginalize() on independent filters through the C view's batched entry point: launch on all, collect on all, the
+    per-filter host work spread over `threads` host threads (engine filters only)."""
+    if not filters:
+        return
+    f0 = filters[0]
+    arr = (C.c_void_p * len(filters))(*[f.h for f in filters])
+    f0._chk(f0._f("marginalize_batch")(arr, C.c_int(len(filters)), C.c_int(int(threads))), "marginalize_batch")
+
+
 class CFilter:
     """MSCKF<_S> surface over a C view.  dtype: np.float32 or np.float64."""
 

@@ -10,6 +10,10 @@ import sys
 from collections import OrderedDict
 
 
+# kernels of the public-API calls that BUILD the workload (propagate / augmentState / prune), not of the timed update
+SETUP_KERNELS = {"k_propagate", "k_augment", "k_gather"}
+
+
 def main(path):
     rows = []
     with open(path, newline="") as f:
@@ -20,7 +24,7 @@ def main(path):
             continue
         name = r["Kernel Name"]
         m = re.search(r"(k_[a-z_0-9]+)", name)
-        if not m:
+        if not m or m.group(1) in SETUP_KERNELS:
             continue
         val = float(r["Metric Value"].replace(",", ""))
         unit = r.get("Metric Unit", "ns")

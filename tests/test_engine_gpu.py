@@ -263,6 +263,28 @@ def test_fused_and_separate_substitution_agree(nf, nc, seq):
     assert dP < 1e-8, dP
 
 
+def test_batched_entry_point_matches_individual_updates():
+    """`msckf_mono_marginalize_batch` (host work on several threads, one stream per filter) gives bit-identical filters to
+    calling marginalize() one by one."""
+    from msckf_mono_b200.cview import marginalize_batch
+    wls = [synth.make_window_workload(n_features=40 + 7 * i, n_clones=10 + i, seq=20 + i) for i in range(6)]
+    one, many = [], []
+    for wl in wls:
+        a, b = make_engine(np.float32), make_engine(np.float32)
+        synth.drive(a, wl, marginalize_last=False)
+        synth.drive(b, wl, marginalize_last=False)
+        one.append(a); many.append(b)
+    for a in one:
+        a.marginalize()
+    marginalize_batch(many, threads=3)
+    for a, b in zip(one, many):
+        assert np.array_equal(a.getCovariance(), b.getCovariance())
+        assert np.array_equal(a.getImuState()["p_I_G"], b.getImuState()["p_I_G"])
+        ra, rb = a.lastReport(), b.lastReport()
+        assert np.array_equal(ra["accepted"], rb["accepted"]) and np.array_equal(ra["gamma"], rb["gamma"])
+        assert a.counters() == b.counters()
+
+
 def test_full_size_properties_stress_fp64():
     """BASELINE config S (2000 features x 60 clones, fp64): size-independent properties (the oracle would take
     minutes here): exact symmetry, positive semi-definiteness, information gain, rank = n - 7 gauge directions."""

@@ -383,7 +383,7 @@ def main():
                      "kernel": dom, "kernel_ms": kern_ms[dom], "peak_source": peak_src, "algorithmic_bytes_per_update": bytes_alg,
                      "whole_update_gbs": bytes_alg / (dev_ms / K * 1e-3) / 1e9,
                      "reference_path_gflop_per_update": algorithmic_flops(N_FEAT, N_CLONES) / 1e9,
-                     "note": "the update is latency-bound (11 short dependent kernels); see DESIGN.md for the per-kernel table",
+                     "note": "the update is latency-bound (11 short kernels, 10 on the critical path); see DESIGN.md for the per-kernel table",
                      "kernel_ms_all": kern_ms},
         "cpu_baseline": {"value": cpu_val, "unit": "updates/s", "cores": 1, "kind": "port",
                          "sample": f"{cpu_n} marginalize() calls of the same {N_FEAT}x{N_CLONES} fp32 workload in {cpu_wall:.1f} s, "

@@ -64,6 +64,23 @@ class TrackBatch:
         return self.off.nbytes + self.obs.nbytes + self.idx.nbytes + (0 if self.pfg is None else self.pfg.nbytes)
 
 
+def update_batch(engines, mode, batches, threads=8):
+    """msckf_b200_update_batch: one update per engine (independent filters), host work on `threads` threads.
+    Returns the per-engine (m, rank, accepted) reports."""
+    n = len(engines)
+    assert n == len(batches)
+    hs = (C.c_void_p * n)(*[e.h for e in engines])
+    trs = (Tracks * n)(*[b.c for b in batches])
+    reps = (Report * n)()
+    accs = []
+    for i, b in enumerate(batches):
+        acc = np.zeros(max(b.n_tracks, 1), dtype=np.int32)
+        reps[i].accepted = acc.ctypes.data_as(C.POINTER(C.c_int))
+        accs.append(acc)
+    check(lib().msckf_b200_update_batch(hs, C.c_int(n), C.c_int(mode), trs, reps, C.c_int(int(threads))), "msckf_b200_update_batch")
+    return [{"m": reps[i].m, "rank": reps[i].rank, "accepted": accs[i][:batches[i].n_tracks]} for i in range(n)]
+
+
 class Engine:
     """owning wrapper of a msckf_b200_engine*; `borrowed` wraps a handle owned by somebody else."""
 

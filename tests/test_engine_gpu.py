@@ -285,6 +285,31 @@ def test_batched_entry_point_matches_individual_updates():
         assert a.counters() == b.counters()
 
 
+def test_c_abi_update_batch_matches_separate_updates():
+    """`msckf_b200_update_batch` on the raw C-ABI: engines whose state was copied from driven filters, the queued batches
+    replayed through the batched entry point -> same m, rank, accept flags and bit-identical covariance as one-by-one."""
+    from msckf_mono_b200 import capi
+    wls = [synth.make_window_workload(n_features=30 + 9 * i, n_clones=9 + i, seq=40 + i) for i in range(5)]
+    engines, batches, ref = [], [], []
+    for wl in wls:
+        f = make_engine(np.float64, max_clones=40, max_tracks=512, max_obs=512 * 30)  # same capacities as capi.Engine's defaults
+        synth.drive(f, wl, marginalize_last=False)
+        off, obs, idx = f.packQueued()
+        src = capi.Engine(np.float64, borrowed=f.engineHandle())
+        e = capi.Engine(np.float64)
+        e.copy_state_from(src)
+        engines.append(e)
+        batches.append(capi.TrackBatch(off, obs, idx, np.float64))
+        f.marginalize()
+        rep = f.lastReport()
+        ref.append((f.getCovariance(), rep["accepted"].copy(), f.counters()))
+    reps = capi.update_batch(engines, capi.MARGINALIZE, batches, threads=4)
+    for e, r, (P, acc, cnt) in zip(engines, reps, ref):
+        assert np.array_equal(r["accepted"].astype(bool), acc.astype(bool))
+        assert r["m"] == cnt["m"] and r["rank"] == cnt["rows_kept"]
+        assert np.array_equal(e.covariance(), P)
+
+
 def test_full_size_properties_stress_fp64():
     """BASELINE config S (2000 features x 60 clones, fp64): size-independent properties (the oracle would take
     minutes here): exact symmetry, positive semi-definiteness, information gain, rank = n - 7 gauge directions."""

@@ -350,7 +350,7 @@ struct Engine : EngineBase {
     mark("begin");
     const int n = 15 + 6 * M, c = 6 * M;
     mb::FeatArgs<S> a;
-    a.n_tracks = N; a.M = M; a.Lmax = Lmax; a.ldp = ldp;
+    a.n_tracks = N; a.M = M; a.Lmax = Lmax; a.ldp = ldp; a.has_yf = 1;
     a.obs_off = d_off; a.obs = d_obs; a.clone_idx = d_idx; a.poses = d_poses; a.P = d_P; a.st = d_st;
     a.pfg = d_pfg; a.counter_snap = d_csnap; a.cm_eff = d_cmeff; a.cm_ok = d_cm; a.tri_ok = d_tri; a.valid = d_valid; a.src = d_src;
     a.pfg_given = (mode == MSCKF_B200_RESIDUALIZE) ? d_pfg_given : nullptr;
@@ -367,7 +367,9 @@ struct Engine : EngineBase {
       mark("k_tri");
     }
     if (mode != MSCKF_B200_TRIANGULATE) {
-      const size_t jsmem = mb::jac_smem_bytes<S>(Lmax, M);
+      size_t jsmem = mb::jac_smem_bytes<S>(Lmax, M, true);
+      a.has_yf = 1;
+      if (jsmem > kSmemBudget) { jsmem = mb::jac_smem_bytes<S>(Lmax, M, false); a.has_yf = 0; }  // longest fp64 tracks: CTA-wide gate only
       if (jsmem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_jac shared memory");
       mb::k_jac<S><<<N, mb::JT, jsmem, stream>>>(a, d_st, mode == MSCKF_B200_RESIDUALIZE ? 1 : 0);
       launches++;

@@ -14,6 +14,7 @@ namespace mb {
 template <class S>
 struct FeatArgs {
   int n_tracks, M, Lmax, ldp;
+  int has_yf;  // k_jac's shared memory includes the single-warp gate Cholesky's copy (dropped at the longest fp64 tracks)
   const int* obs_off;    // [N+1]
   const S* obs;          // [sumL*2] normalised image coordinates
   const int* clone_idx;  // [sumL] positional index of the observing clone
@@ -372,11 +373,11 @@ __device__ __forceinline__ bool chol_warp(S* Yf, const S* dg, int rho, int lane)
 }
 
 template <class S>
-__host__ __device__ inline size_t jac_smem_bytes(int L, int M) {
+__host__ __device__ inline size_t jac_smem_bytes(int L, int M, bool with_yf = true) {
   // bar 16 | poses M*8 S | U64 6L doubles | X 12L | r 2L | V 6L | W 6L | F 6L | Ypacked L(2L+1)  (S) | pad |
   // Yf 64 x 68 + dg 64 (S): the single-warp gate Cholesky's row-major copy
   return 16 + sizeof(S) * kPoseStride * (size_t)M + 16 + sizeof(double) * 6 * (size_t)L +
-         sizeof(S) * ((size_t)32 * L + (size_t)L * (2 * L + 1)) + 32 + sizeof(S) * ((size_t)kCholRows * kCholLd + kCholRows);
+         sizeof(S) * ((size_t)32 * L + (size_t)L * (2 * L + 1)) + 32 + (with_yf ? sizeof(S) * ((size_t)kCholRows * kCholLd + kCholRows) : 0);
 }
 
 // Ordered stacking (msckf.h:433-445): the exclusive prefix sum of the accepted blocks' row counts, computed by whichever
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   S* Y = Fv + 3 * L2;
   S* Yf = reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(Y + (size_t)L * (L2 + 1)) + 15) & ~uintptr_t(15));  // [64][68]
   S* dgv = Yf + kCholRows * kCholLd;  // [64]
-  const bool warp_chol = (L2 - 3 + 1 <= kCholRows);  // the gate matrix and its right-hand side fit the single-warp form
+  const bool warp_chol = a.has_yf && (L2 - 3 + 1 <= kCholRows);  // the gate matrix and its right-hand side fit the single-warp form
   const int* idx = a.clone_idx + o0;
   const S* z = a.obs + 2 * (size_t)o0;
   const DevState<S>* st = a.st;

@@ -310,6 +310,25 @@ def test_c_abi_update_batch_matches_separate_updates():
         assert np.array_equal(e.covariance(), P)
 
 
+def test_maximum_track_length_98_fp64(oracle_lib):
+    """The reference's chi-square table has 99 entries (msckf.h:91), so 98 observations per track is the longest track it
+    can gate.  98 clones -> n = 603: the large-window tail kernel (blocks of 16) and the CTA-wide gate (the single-warp
+    copy does not fit next to a 196 x 196 packed matrix in fp64) -- paths the other tests do not reach."""
+    wl = synth.make_window_workload(n_features=24, n_clones=98, seq=11, imu_per_frame=2)  # 10 ms frames: everything stays in view
+    g = make_engine(np.float64, max_clones=104, max_tracks=64, max_obs=64 * 98)
+    o = make_oracle(oracle_lib, np.float64, drop_null_rows=True)
+    rg, ro = _drive_pair(g, o, wl)
+    sg, so = _assert_bookkeeping_equal(g, o, rg, ro)
+    rep_g, rep_o = g.lastReport(), o.lastReport()
+    assert rep_g["rows"].max() == 2 * 98 - 3
+    ddx = rel(g.lastDeltaX(), o.lastDeltaX())
+    dP = np.abs(sg["P"] - so["P"]).max() / np.abs(so["P"]).max()
+    print(f"L = 98, n = 603: dx rel {ddx:.2e}, P rel {dP:.2e}, gamma rel {rel(rep_g['gamma'], rep_o['gamma']):.2e}, rows kept {g.counters()['rows_kept']}")
+    assert rel(rep_g["gamma"], rep_o["gamma"]) < 1e-7
+    assert ddx < 1e-5 and dP < 1e-6
+    assert g.counters()["rows_kept"] == o.counters()["rows_kept"]
+
+
 def test_full_size_properties_stress_fp64():
     """BASELINE config S (2000 features x 60 clones, fp64): size-independent properties (the oracle would take
     minutes here): exact symmetry, positive semi-definiteness, information gain, rank = n - 7 gauge directions."""

@@ -255,17 +255,25 @@ def main():
         return
     # ---------------------------------------------------------------- end-to-end through the class surface
     filts = [ready_filter(DTYPE, seq=200 + rank * 1000 + i, device=local_rank) for i in range(K + W)]
-    e2e_times = []
+    e2e_times, e2e_parts = [], []
     for i, f in enumerate(filts):
         flush_l2()
         t0 = time.perf_counter()
-        f.marginalize()            # host pack + H2D + kernels + D2H report
+        f.marginalizeLaunch()      # marginalize() = launch (host pack + one H2D copy + graph launch) ...
+        t1 = time.perf_counter()
+        f.marginalizeCollect()     # ... + collect (wait for the kernels, one D2H report copy, host bookkeeping)
+        t2 = time.perf_counter()
         st = f.getImuState()       # D2H of the corrected state (the step's result)
         dt = time.perf_counter() - t0
         if i >= W:
             e2e_times.append(dt)
+            e2e_parts.append((t1 - t0, t2 - t1, t0 + dt - t2))
     assert np.isfinite(st["p_I_G"]).all()
     e2e_s = float(np.sum(e2e_times))
+    if rank == 0:
+        pl, pc, ps = (1e6 * float(np.mean([p[j] for p in e2e_parts])) for j in range(3))
+        print(f"e2e breakdown (us per update): launch {pl:.0f} (pack + H2D + graph launch), collect {pc:.0f} (kernels + D2H + bookkeeping), "
+              f"getImuState {ps:.0f}", file=sys.stderr)
     up16 = lambda x: (x + 15) & ~15  # the engine's packed report block: (m, rank) | 5 int flags per track | p_f_G | gamma, one D2H copy
     rep_bytes = 16 + 5 * up16(4 * N_FEAT) + up16(4 * 3 * N_FEAT) + up16(4 * N_FEAT)
     state_bytes = 1192 + 8 * 4 * N_CLONES  # sizeof(DevState<float>) + clone poses

@@ -11,7 +11,8 @@
 // (ncu source view, profiles/) and acted upon:
 //   * instruction count per pivot is what the diagonal block costs: the two factorisations run in two warps (A polls
 //     G's decision for the pivot through shared memory), two more warps build the inverses of the two factors one
-//     pivot behind, rsqrt is a float seed + two Newton steps, the dot products read 8 columns per step with 16-byte loads;
+//     pivot behind, rsqrt is a float seed + two Newton steps, the dot products read 16 columns per round trip with 16-byte
+//     loads and are formed one pivot ahead (look-ahead), so that a pivot starts with one shuffle and one FMA;
 //   * instruction fetch: hand-unrolled register-resident forms (~50-100 KB of straight-line code that runs once per
 //     block) are bound by instruction-cache misses at ~15 cycles per instruction -- every hot loop here is ROLLED;
 //   * work on the critical path: the panel below a diagonal block is X = A_panel L_kk^-T.  With L_kk^-1 at hand the
@@ -19,7 +20,9 @@
 //     the 8 CTAs (no redundant solves) and exchanged through L2 (a scratch panel every CTA reads back after the cluster
 //     barrier: ~64 B/clk per SM, against ~20 B/clk for pushing it into 8 shared memories through DSMEM);
 //   * shared-memory bank conflicts: tiles are dealt so that the lanes of a warp read neighbouring columns.
-// Three cluster barriers (release/acquire at cluster scope) per block order the phases.
+//   * overlap: CTA 0 forms the leading 32 x 32 tile of the trailing update itself and factorises the NEXT diagonal block
+//     while CTAs 1..7 run the rest of the trailing update and their share of the substitution.
+// Two cluster barriers (release/acquire at cluster scope) per block order the phases.
 #pragma once
 #include <cooperative_groups.h>
 #include "common.cuh"

@@ -477,6 +477,10 @@ class MSCKF {
       const auto& tr = tracks[t];
       if (tr.cam_state_indices.size() != tr.observations.size())
         throw std::logic_error("track observations and clone indices differ in number");
+      // the reference clears the queue in update() only (:218): finish() after a marginalize() would re-residualise the
+      // last update's tracks with their old positional indices (undefined behaviour there once clones were pruned)
+      for (size_t ci : tr.cam_state_indices)
+        if (ci >= cam_states_.size()) throw std::logic_error("stale residualisation queue: clone index out of range (reference: undefined behaviour)");
       for (size_t i = 0; i < tr.observations.size(); ++i) {
         pk_obs_[2 * (pk_off_[t] + i)] = tr.observations[i](0);
         pk_obs_[2 * (pk_off_[t] + i) + 1] = tr.observations[i](1);

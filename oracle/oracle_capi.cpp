@@ -158,7 +158,15 @@ struct Impl : Base {
 };
 }  // namespace
 
+// exceptions (the stale-queue guard) must not cross the C boundary: -1 + msckf_oracle_last_error()
+static thread_local std::string g_oracle_err;
+template <class F>
+static int oguard(F&& f) {
+  try { f(); return 0; } catch (const std::exception& e) { g_oracle_err = e.what(); return -1; }
+}
+
 extern "C" {
+const char* msckf_oracle_last_error(void) { return g_oracle_err.c_str(); }
 int msckf_oracle_create(int dtype, void** out) {
   Base* b = (dtype == 0) ? (Base*)new Impl<float>() : (Base*)new Impl<double>();
   *out = b;
@@ -170,10 +178,10 @@ int msckf_oracle_propagate(void* h, const double* m) { ((Base*)h)->propagate(m);
 int msckf_oracle_augment_state(void* h, int id, double t) { ((Base*)h)->augment(id, t); return 0; }
 int msckf_oracle_update(void* h, const double* z, const uint64_t* ids, int n) { ((Base*)h)->update(z, ids, n); return 0; }
 int msckf_oracle_add_features(void* h, const double* z, const uint64_t* ids, int n) { ((Base*)h)->add(z, ids, n); return 0; }
-int msckf_oracle_marginalize(void* h) { ((Base*)h)->marginalize(); return 0; }
+int msckf_oracle_marginalize(void* h) { return oguard([&] { ((Base*)h)->marginalize(); }); }
 int msckf_oracle_prune_redundant_states(void* h) { ((Base*)h)->prune_redundant(); return 0; }
 int msckf_oracle_prune_empty_states(void* h) { ((Base*)h)->prune_empty(); return 0; }
-int msckf_oracle_finish(void* h) { ((Base*)h)->finish(); return 0; }
+int msckf_oracle_finish(void* h) { return oguard([&] { ((Base*)h)->finish(); }); }
 int msckf_oracle_get_num_cam_states(void* h) { return ((Base*)h)->num_cam(); }
 int msckf_oracle_get_imu_state(void* h, double* out) { ((Base*)h)->imu_state(out); return 0; }
 int msckf_oracle_get_cam_states(void* h, double* poses, int* ids, double* times) { ((Base*)h)->cam_states(poses, ids, times); return 0; }

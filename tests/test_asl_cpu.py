@@ -61,3 +61,33 @@ def test_timestamps_are_ordered_and_imu_precedes_its_frame(mav0):
 def test_player_rejects_missing_folder(engine_lib):
     with pytest.raises(RuntimeError):
         asl.run_player("/nonexistent/mav0", dry_run=True)
+
+
+def test_player_call_sequence_on_cpu_against_the_oracle(mav0, oracle_lib, tmp_path):
+    """The compiled player's host logic without a GPU: asl_player.cpp linked against tests/stub/stub_engine.cpp (a fake
+    of the C-ABI with no numerics) must hand the class the same frames, IMU readings and tracked / new feature split as
+    `synth.drive` hands the oracle: the clone-window size per frame (update / addFeatures / pruneEmptyStates bookkeeping)
+    is then identical.  pruneRedundantStates is off here: its decisions depend on poses, which the fake does not compute."""
+    import subprocess
+    from tests.common import ROOT, make_oracle
+    wl, m = mav0
+    exe = ROOT / "tests" / "stub" / "asl_player_stub"
+    src = [ROOT / "msckf_mono_b200" / "asl" / "asl_player.cpp", ROOT / "tests" / "stub" / "stub_engine.cpp",
+           ROOT / "msckf_mono_b200" / "asl" / "asl_io.hpp", ROOT / "include" / "msckf_mono" / "msckf.h"]
+    if (not exe.exists()) or any(s.stat().st_mtime > exe.stat().st_mtime for s in src):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", f"-I{ROOT / 'include'}", f"-I{ROOT / 'msckf_mono_b200' / 'asl'}",
+                               str(src[0]), str(src[1]), "-o", str(exe)])
+    out = tmp_path / "traj_stub.csv"
+    r = subprocess.run([str(exe), "--mav0", m, "--dtype", "f64", "--out", str(out), "--prune-redundant", "0", "--state-id", "frame"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    import json
+    summary = json.loads(r.stdout.strip().splitlines()[-1])
+    frames = wl["frames"]
+    assert summary["frames"] == len(frames) and summary["imu_readings"] == sum(len(fr["imu"]) for fr in frames)
+    tr = asl.read_trajectory(str(out))
+    o = make_oracle(oracle_lib, np.float64)
+    ncl = []
+    synth.drive(o, wl, prune_redundant=False, on_frame=lambda k, f: ncl.append(f.getNumCamStates()))
+    assert np.array_equal(tr["n_clones"], np.array(ncl))
+    assert np.array_equal(tr["t_ns"], np.array([int(l.split(",")[0]) for l in open(os.path.join(m, "cam0/data.csv")) if not l.startswith("#")]))

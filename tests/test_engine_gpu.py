@@ -331,6 +331,23 @@ def test_maximum_track_length_98_fp64(oracle_lib):
     assert o.counters()["rows_kept"] in (603 - 7, 603 - 6) and g.counters()["rows_kept"] in (603 - 7, 603 - 6)
 
 
+def test_engine_update_is_invariant_to_track_order():
+    """Same property as tests/test_oracle.py::test_update_is_invariant_to_track_order, on the engine alone (isotropic
+    pixel noise): permuting the features permutes the per-track outputs and leaves the update unchanged."""
+    from tests.test_oracle import _permuted
+    wl = synth.make_window_workload(n_features=40, n_clones=12, seq=22, isotropic=True)
+    perm = np.random.default_rng(22).permutation(40)
+    a, b = make_engine(np.float64), make_engine(np.float64)
+    ra, rb = run_collect(a, wl), run_collect(b, _permuted(wl, perm))
+    assert ra["valid"].all() and np.array_equal(np.asarray(ra["accepted"])[perm], rb["accepted"])
+    ddx = rel(a.lastDeltaX(), b.lastDeltaX())
+    Pa, Pb = a.getCovariance(), b.getCovariance()
+    dP = np.abs(Pa - Pb).max() / np.abs(Pa).max()
+    print(f"engine order invariance: dx rel {ddx:.2e}, P rel {dP:.2e}")
+    assert ddx < 1e-6 and dP < 1e-8
+    assert rel(np.asarray(a.lastReport()["gamma"])[perm], b.lastReport()["gamma"]) < 1e-9
+
+
 def test_full_size_properties_stress_fp64():
     """BASELINE config S (2000 features x 60 clones, fp64): size-independent properties (the oracle would take
     minutes here): exact symmetry, positive semi-definiteness, information gain, rank = n - 7 gauge directions."""

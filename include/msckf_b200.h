@@ -29,7 +29,10 @@ enum msckf_b200_status {
   MSCKF_B200_ERR_CAPACITY = -2,  /* more clones / tracks / observations than msckf_b200_create reserved */
   MSCKF_B200_ERR_ARG = -3,       /* invalid argument (e.g. track longer than 98 observations, msckf.h:91) */
   MSCKF_B200_ERR_NO_DEVICE = -4, /* no CUDA device: the engine never computes on the CPU */
-  MSCKF_B200_ERR_STATE = -5      /* call order violated */
+  MSCKF_B200_ERR_STATE = -5,     /* call order violated */
+  MSCKF_B200_ERR_NUMERIC = -6    /* the update produced a non-finite delta-x or covariance entry.  The update HAS been applied, like in
+                                    the reference (whose only anomaly handling is a print, msckf.h:1405-1409): returned by _fetch
+                                    after the report was filled, so the caller decides (the class shim prints and carries on) */
 };
 enum msckf_b200_mode {
   MSCKF_B200_MARGINALIZE = 0, /* MSCKF::marginalize() msckf.h:336-449: loop A + loop B + measurementUpdate */
@@ -42,10 +45,14 @@ typedef struct msckf_b200_engine msckf_b200_engine;
 typedef struct {
   int dtype;       /* msckf_b200_dtype */
   int device;      /* CUDA device ordinal */
-  int max_clones;  /* capacity M_max (covariance is (15+6*M_max)^2) */
-  int max_tracks;  /* capacity of one track batch */
-  int max_obs;     /* capacity of one batch's total observation count */
+  int max_clones;  /* initial capacity M_max (covariance is (15+6*M_max)^2) */
+  int max_tracks;  /* initial capacity of one track batch */
+  int max_obs;     /* initial capacity of one batch's total observation count */
 } msckf_b200_config;
+/* The three capacities are INITIAL sizes: like the reference, whose window and track lists are unbounded std::vectors, the
+ * engine grows its device buffers on demand (x2, contents preserved).  Hard limits that remain: 98 observations per track
+ * (the reference's chi-square table has 99 entries, msckf.h:91 -- longer tracks index past it there) and the window the
+ * tail kernel's shared-memory panels can hold (about 135 clones): both fail with MSCKF_B200_ERR_CAPACITY / _ARG. */
 
 /* One batch of feature tracks, flat SoA (types.h:102-113 featureTrackToResidualize without the clone copies:
  * the clone poses are device resident and addressed by POSITION in the sliding window, msckf.h:1481). */
@@ -68,6 +75,7 @@ typedef struct {
   int m;         /* out: stacked rows of accepted tracks (stack_counter, msckf.h:443) */
   int rank;      /* out: independent rows kept by the compression */
 } msckf_b200_report;
+/* (a non-finite result is signalled by _fetch returning MSCKF_B200_ERR_NUMERIC, with the report filled) */
 
 int msckf_b200_create(const msckf_b200_config* cfg, msckf_b200_engine** out);
 int msckf_b200_destroy(msckf_b200_engine* e);
@@ -78,12 +86,21 @@ int msckf_b200_destroy(msckf_b200_engine* e);
 int msckf_b200_initialize(msckf_b200_engine* e, const void* camera, const void* noise, const void* params, const void* imu_state);
 /* MSCKF::propagate msckf.h:101-145.  reading: omega[3], a[3], dT */
 int msckf_b200_propagate(msckf_b200_engine* e, const void* reading);
+/* k consecutive propagate() calls (readings: [k][7] scalars) in one kernel launch per 16 readings; same arithmetic, reading
+ * by reading.  The class shim queues the IMU readings that arrive between two images (src/ros_interface.cpp:92-97) */
+int msckf_b200_propagate_n(msckf_b200_engine* e, const void* readings, int k);
 /* MSCKF::augmentState msckf.h:148-212 (numeric part: clone pose + covariance augmentation) */
 int msckf_b200_augment(msckf_b200_engine* e);
 /* marginalize / pruneRedundantStates numerics, asynchronous on the handle's stream.  The input arrays are
- * copied to pinned staging before return; results are fetched (and the stream synchronised) by _fetch. */
+ * copied to pinned staging before return; results are fetched (and the stream synchronised) by _fetch.
+ * A track with a single observation cannot be triangulated or projected (2L - 3 < 1 rows): it is reported as rejected
+ * (cm_ok = tri_ok = valid = accepted = 0), not as an error. */
 int msckf_b200_update_async(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks);
 int msckf_b200_fetch(msckf_b200_engine* e, msckf_b200_report* report);
+/* Zero-copy packing: host pointers INTO the engine's pinned input block for a batch of n_tracks tracks / n_obs observations
+ * (out->obs_offset, ->obs, ->clone_index, ->p_f_G; out->n_tracks = n_tracks).  The caller fills them and passes the same struct
+ * to _update / _update_async / _stage, which then skips its own copy.  Valid until the next call on this handle. */
+int msckf_b200_input_buffer(msckf_b200_engine* e, int n_tracks, int n_obs, msckf_b200_tracks* out);
 /* update_async split in two: _stage validates and copies the batch into HBM, _launch enqueues the kernels
  * (bench.py times _launch alone: "inputs already resident in HBM") */
 int msckf_b200_stage(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks);
@@ -96,14 +113,36 @@ int msckf_b200_kernel_times(msckf_b200_engine* e, float* ms, const char** names,
 int msckf_b200_tail_profile(msckf_b200_engine* e, unsigned long long* out, int cap);
 /* update_async + fetch */
 int msckf_b200_update(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tracks, msckf_b200_report* report);
-/* Batched variant for independent filters (sequences / Monte-Carlo trials sharing one GPU): update_async on
- * every engine, then fetch on every engine, the per-filter host work (validation, packing, launch, report) spread over
- * `threads` host threads.  Every filter runs on its own stream, so their kernels overlap on the device.  Results are
- * identical to n separate msckf_b200_update calls.  reports may be NULL.  Returns the first non-zero status. */
+/* ---- device-side batches of independent filters (sequences / Monte-Carlo trials sharing one GPU) ----------
+ * A batch groups n engines (same dtype, same device).  One update of the whole group is ONE launch per kernel -- the filter
+ * index rides in blockIdx.z, one thread-block cluster per filter runs the serial tail -- replayed as ONE CUDA graph, with ONE
+ * packed host->device copy of all track batches and ONE packed device->host copy of all reports.  Results are bit-identical
+ * to n separate msckf_b200_update calls.  While a batch exists its engines share the batch's stream (their other calls --
+ * propagate, augment, prune, getters -- stay valid and are ordered with the batch's updates); destroying the batch gives
+ * every engine its own stream back.  An engine belongs to at most one batch. */
+typedef struct msckf_b200_batch msckf_b200_batch;
+int msckf_b200_batch_create(msckf_b200_engine** engines, int n, msckf_b200_batch** out);
+int msckf_b200_batch_destroy(msckf_b200_batch* b);
+/* tracks[n] / reports[n]: one per engine, in the order given to _create; reports may be NULL.  `threads` host threads share
+ * the validation and packing of the n track batches (<= 1: the calling thread does all of it). */
+int msckf_b200_batch_update_async(msckf_b200_batch* b, int mode, const msckf_b200_tracks* tracks, int threads);
+int msckf_b200_batch_fetch(msckf_b200_batch* b, msckf_b200_report* reports);
+int msckf_b200_batch_update(msckf_b200_batch* b, int mode, const msckf_b200_tracks* tracks, msckf_b200_report* reports, int threads);
+/* the same split as _stage / _launch / _launch_timed of a single engine (bench.py: inputs resident in HBM) */
+int msckf_b200_batch_stage(msckf_b200_batch* b, int mode, const msckf_b200_tracks* tracks, int threads);
+int msckf_b200_batch_launch(msckf_b200_batch* b);
+int msckf_b200_batch_launch_timed(msckf_b200_batch* b, float* ms);
+/* per-kernel device times of the last batch launch (option key 1 of the FIRST engine set); returns the count */
+int msckf_b200_batch_kernel_times(msckf_b200_batch* b, float* ms, const char** names, int cap);
+long long msckf_b200_batch_launch_count(const msckf_b200_batch* b);
+void* msckf_b200_batch_stream(msckf_b200_batch* b);
+/* Convenience: one update on each of n engines through a batch.  If the engines already form a batch (in this order) it is
+ * used; otherwise a temporary one is created and destroyed around the call.  Returns the first non-zero status. */
 int msckf_b200_update_batch(msckf_b200_engine** engines, int n, int mode, const msckf_b200_tracks* tracks, msckf_b200_report* reports,
                             int threads);
 /* covariance / pose gather of pruneEmptyStates msckf.h:685-761 and pruneRedundantStates :616-681:
- * keep[] = ascending positional indices of the clones that survive */
+ * keep[] = ascending positional indices of the clones that survive (n_keep = 0: only the IMU block stays).
+ * Asynchronous: keep[] travels as a kernel argument, nothing is synchronised and captured graphs stay valid. */
 int msckf_b200_prune(msckf_b200_engine* e, const int* keep, int n_keep);
 
 int msckf_b200_num_clones(msckf_b200_engine* e);
@@ -119,7 +158,8 @@ int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap);
  *              1 = record per-kernel CUDA events in _launch (profiling aid, default off);
  *              2 = replay the update's kernel sequence as a CUDA graph when the batch signature repeats (default on);
  *              3 = fuse the forward substitution into the blocked Cholesky of the tail kernel where the window allows it
- *                  (15 + 6M <= 255; default on; 0 = always run it as a separate sweep -- same results up to rounding) */
+ *                  (15 + 6M <= 255; default on; 0 = always run it as a separate sweep -- same results up to rounding);
+ *              4 = launch the update's kernels with programmatic dependent launch (default on) */
 int msckf_b200_set_option(msckf_b200_engine* e, int key, double value);
 /* checkpoint / resume: copy the complete filter state of src into dst (same dtype and capacities) */
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src);

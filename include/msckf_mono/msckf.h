@@ -36,8 +36,20 @@ class MSCKF {
   MSCKF_B200_ALIGNED_NEW
   MSCKF() {}
   ~MSCKF() { if (engine_) msckf_b200_destroy(engine_); }
+  // The filter owns device memory: it moves (so that filters can live in containers and be returned by value) but does not
+  // copy -- the reference's implicit copy duplicated a few KB of host state, here it would have to duplicate a device-resident
+  // covariance behind the caller's back (use msckf_b200_copy_state on engine() for an explicit checkpoint).
   MSCKF(const MSCKF&) = delete;
   MSCKF& operator=(const MSCKF&) = delete;
+  MSCKF(MSCKF&& o) noexcept { moveFrom(o); }
+  MSCKF& operator=(MSCKF&& o) noexcept {
+    if (this != &o) {
+      if (engine_) msckf_b200_destroy(engine_);
+      engine_ = nullptr;
+      moveFrom(o);
+    }
+    return *this;
+  }
 
   // Engine capacities (call before initialize; 0 = derive from MSCKFParams).
   void setEngineOptions(int device, int max_clones = 0, int max_tracks = 0, int max_obs = 0) {
@@ -62,9 +74,10 @@ class MSCKF {
     cfg.dtype = sizeof(_S) == 4 ? MSCKF_B200_F32 : MSCKF_B200_F64;
     cfg.device = device_;
     const int lcap = std::min(std::max(msckf_params.max_track_length, 2), 98);  // chi-square table has 99 entries (ref :91)
-    cfg.max_clones = cap_clones_ > 0 ? cap_clones_ : std::min(std::max(msckf_params.max_cam_states, lcap), 98) + 8;
+    // initial sizes only: like the reference's std::vectors, the engine grows on demand (window, tracks, observations)
+    cfg.max_clones = cap_clones_ > 0 ? cap_clones_ : std::min(std::max(msckf_params.max_cam_states + 8, 32), 104);
     cfg.max_tracks = cap_tracks_ > 0 ? cap_tracks_ : 512;
-    cfg.max_obs = cap_obs_ > 0 ? cap_obs_ : cfg.max_tracks * lcap;
+    cfg.max_obs = cap_obs_ > 0 ? cap_obs_ : cfg.max_tracks * std::min(lcap, 32);
     check(msckf_b200_create(&cfg, &engine_), "msckf_b200_create");
     _S cam[7] = {camera.q_CI.x(), camera.q_CI.y(), camera.q_CI.z(), camera.q_CI.w(), camera.p_C_I(0), camera.p_C_I(1), camera.p_C_I(2)};
     std::vector<_S> nz(2 + 144 + 225);
@@ -80,21 +93,25 @@ class MSCKF {
     im[15] = imu_state.q_IG.x(); im[16] = imu_state.q_IG.y(); im[17] = imu_state.q_IG.z(); im[18] = imu_state.q_IG.w();
     check(msckf_b200_initialize(engine_, cam, nz.data(), pr, im), "msckf_b200_initialize");
     state_dirty_ = false;
+    imu_queue_.clear();
     epoch_ = 0; epoch_at_queue_ = 0;
   }
 
-  // ref :101-145
+  // ref :101-145.  The reading is queued on the host; the queue is handed to the device in one call
+  // (msckf_b200_propagate_n: one kernel launch for up to 16 readings, same arithmetic reading by reading) by whichever
+  // member function next needs the device state -- augmentState() in the reference's ROS loop (src/ros_interface.cpp:92-108),
+  // getImuState() in its ASL loop (datasets/asl_msckf.cpp:229-234, one reading per call there).
   void propagate(imuReading<_S>& measurement_) {
     const _S r[7] = {measurement_.omega(0), measurement_.omega(1), measurement_.omega(2), measurement_.a(0), measurement_.a(1),
                      measurement_.a(2), measurement_.dT};
-    check(msckf_b200_propagate(engine_, r), "msckf_b200_propagate");
+    imu_queue_.insert(imu_queue_.end(), r, r + 7);
     state_dirty_ = true;
   }
 
   // ref :148-212
   void augmentState(const int& state_id, const _S& time) {
     map_.clear();
-    check(msckf_b200_augment(engine_), "msckf_b200_augment");
+    check(msckf_b200_augment(eng()), "msckf_b200_augment");
     camState<_S> cam_state;
     cam_state.last_correlated_id = -1;
     cam_state.time = time;
@@ -174,36 +191,8 @@ class MSCKF {
 
   // ref :336-449.  Loop A, loop B, gating, compression and the Kalman update all run on the device.
   void marginalize() {
-    last_report_.clear();
-    if (feature_tracks_to_residualize_.empty()) return;
-    if (epoch_at_queue_ != epoch_)
-      throw std::logic_error("msckf_mono::MSCKF::marginalize: a measurement update was applied between update()/finish() and "
-                             "marginalize(); the queued tracks' clone snapshots (ref :250) would differ from the device state");
-    packTracks(feature_tracks_to_residualize_);
-    const int N = (int)feature_tracks_to_residualize_.size();
-    msckf_b200_tracks tr;
-    tr.n_tracks = N; tr.obs_offset = pk_off_.data(); tr.obs = pk_obs_.data(); tr.clone_index = pk_idx_.data(); tr.p_f_G = nullptr;
-    last_report_.resize(N);
-    rp_cm_.resize(N); rp_tri_.resize(N); rp_valid_.resize(N); rp_acc_.resize(N); rp_gamma_.resize(N); rp_pfg_.resize(3 * (size_t)N);
-    msckf_b200_report rep;
-    rep.cm_ok = rp_cm_.data(); rep.tri_ok = rp_tri_.data(); rep.valid = rp_valid_.data(); rep.accepted = rp_acc_.data();
-    rep.gamma = rp_gamma_.data(); rep.p_f_G = rp_pfg_.data();
-    check(msckf_b200_update(engine_, MSCKF_B200_MARGINALIZE, &tr, &rep), "msckf_b200_update(MARGINALIZE)");
-    for (int t = 0; t < N; ++t) {
-      auto& track = feature_tracks_to_residualize_[t];
-      TrackReport& r = last_report_[t];
-      r.cm_ok = rp_cm_[t]; r.tri_ok = rp_tri_[t]; r.valid = rp_valid_[t]; r.accepted = rp_acc_[t]; r.gamma = rp_gamma_[t];
-      for (int k = 0; k < 3; ++k) r.p_f_G(k) = rp_pfg_[3 * (size_t)t + k];
-      r.rows = r.accepted ? (2 * (int)track.observations.size() - 3) : 0;
-      if (r.valid) {  // ref :368-372
-        track.initialized = true;
-        track.p_f_G = r.p_f_G;
-        map_.push_back(r.p_f_G);
-      }
-    }
-    last_m_ = rep.m; last_rank_ = rep.rank;
-    if (rep.m > 0) epoch_++;
-    state_dirty_ = true;
+    marginalizeLaunch();
+    marginalizeCollect();
   }
 
   // ref :453-682
@@ -246,14 +235,13 @@ class MSCKF {
       }
     }
     if (!tri_batch.empty()) {
-      packTracks(tri_batch);
-      const int N = (int)tri_batch.size();
       msckf_b200_tracks tr;
-      tr.n_tracks = N; tr.obs_offset = pk_off_.data(); tr.obs = pk_obs_.data(); tr.clone_index = pk_idx_.data(); tr.p_f_G = nullptr;
+      packTracks(tri_batch, nullptr, tr);
+      const int N = (int)tri_batch.size();
       rp_cm_.resize(N); rp_tri_.resize(N); rp_pfg_.resize(3 * (size_t)N);
       msckf_b200_report rep = {};
       rep.cm_ok = rp_cm_.data(); rep.tri_ok = rp_tri_.data(); rep.p_f_G = rp_pfg_.data();
-      check(msckf_b200_update(engine_, MSCKF_B200_TRIANGULATE, &tr, &rep), "msckf_b200_update(TRIANGULATE)");
+      check(msckf_b200_update(eng(), MSCKF_B200_TRIANGULATE, &tr, &rep), "msckf_b200_update(TRIANGULATE)");
       for (int k = 0; k < N; ++k) {
         auto& feature = feature_tracks_[tri_feat[k]];
         // checkMotion on fewer than two clones is false (ref :982-984)
@@ -307,14 +295,10 @@ class MSCKF {
       }
     }
     if (!batch.empty()) {
-      packTracks(batch);
-      const int N = (int)batch.size();
-      std::vector<_S> pf(3 * (size_t)N);
-      for (int k = 0; k < N; ++k) for (int c = 0; c < 3; ++c) pf[3 * (size_t)k + c] = batch[k].p_f_G(c);
       msckf_b200_tracks tr;
-      tr.n_tracks = N; tr.obs_offset = pk_off_.data(); tr.obs = pk_obs_.data(); tr.clone_index = pk_idx_.data(); tr.p_f_G = pf.data();
+      packTracks(batch, &batch, tr);
       msckf_b200_report rep = {};
-      check(msckf_b200_update(engine_, MSCKF_B200_RESIDUALIZE, &tr, &rep), "msckf_b200_update(RESIDUALIZE)");
+      checkNumeric(msckf_b200_update(eng(), MSCKF_B200_RESIDUALIZE, &tr, &rep), "msckf_b200_update(RESIDUALIZE)");
       if (rep.m > 0) epoch_++;
       state_dirty_ = true;
     }
@@ -328,7 +312,7 @@ class MSCKF {
       else { keep.push_back((int)pos); kept.push_back(cam_states_[pos]); }
     }
     if (keep.size() != cam_states_.size()) {
-      check(msckf_b200_prune(engine_, keep.data(), (int)keep.size()), "msckf_b200_prune");
+      check(msckf_b200_prune(eng(), keep.data(), (int)keep.size()), "msckf_b200_prune");
       cam_states_.swap(kept);
     }
   }
@@ -349,7 +333,7 @@ class MSCKF {
     cam_states_.erase(cam_states_.begin(), cam_states_.begin() + ndel);
     std::vector<int> keep;
     for (int i = ndel; i < num_cam_states; ++i) keep.push_back(i);
-    check(msckf_b200_prune(engine_, keep.data(), (int)keep.size()), "msckf_b200_prune");
+    check(msckf_b200_prune(eng(), keep.data(), (int)keep.size()), "msckf_b200_prune");
   }
 
   // ref :765-807
@@ -382,7 +366,7 @@ class MSCKF {
   inline aligned_vector<Vector3<_S>> getMap() { return map_; }
   inline Camera<_S> getCamera() { return camera_; }
   inline camState<_S> getCamState(size_t i) { refreshState(); return cam_states_[i]; }
-  inline std::vector<camState<_S>> getCamStates() { refreshState(); return cam_states_; }
+  inline std::vector<camState<_S>> getCamStates() const { refreshState(); return cam_states_; }  // const like ref :835
   inline std::vector<camState<_S>> getPrunedStates() {
     std::sort(pruned_states_.begin(), pruned_states_.end(), [](const camState<_S>& a, const camState<_S>& b) { return a.state_id < b.state_id; });
     return pruned_states_;
@@ -395,44 +379,58 @@ class MSCKF {
   int lastRank() const { return last_rank_; }
   const std::vector<size_t>& trackedFeatureIds() const { return tracked_feature_ids_; }
   const std::vector<featureTrackToResidualize<_S>>& tracksToResidualize() const { return feature_tracks_to_residualize_; }
-  msckf_b200_engine* engine() { return engine_; }
+  msckf_b200_engine* engine() { return eng(); }  // (queued IMU readings are handed over first)
   // full (15+6M)^2 covariance, row-major (the reference keeps it private in three blocks, ref :52-54)
   std::vector<_S> getCovariance() {
     const size_t n = 15 + 6 * cam_states_.size();
     std::vector<_S> P(n * n);
-    check(msckf_b200_get_covariance(engine_, P.data()) < 0 ? -1 : 0, "msckf_b200_get_covariance");
+    check(msckf_b200_get_covariance(eng(), P.data()) < 0 ? -1 : 0, "msckf_b200_get_covariance");
     return P;
   }
-  // marginalize() split in two for pipelining many filters over one GPU: launch, then collect.
+  // marginalize() = launch + collect (kept separate for pipelining and for batches of filters, MSCKFBatch below).
   void marginalizeLaunch() {
-    last_report_.clear();
-    launch_pending_ = false;
-    if (feature_tracks_to_residualize_.empty()) return;
-    if (epoch_at_queue_ != epoch_) throw std::logic_error("marginalizeLaunch: state changed since update()");
-    packTracks(feature_tracks_to_residualize_);
     msckf_b200_tracks tr;
-    tr.n_tracks = (int)feature_tracks_to_residualize_.size(); tr.obs_offset = pk_off_.data(); tr.obs = pk_obs_.data();
-    tr.clone_index = pk_idx_.data(); tr.p_f_G = nullptr;
-    check(msckf_b200_update_async(engine_, MSCKF_B200_MARGINALIZE, &tr), "msckf_b200_update_async");
+    if (!marginalizePrepare(tr, true)) return;
+    check(msckf_b200_update_async(eng(), MSCKF_B200_MARGINALIZE, &tr), "msckf_b200_update_async");
     launch_pending_ = true;
   }
   void marginalizeCollect() {
     if (!launch_pending_) return;
     launch_pending_ = false;
+    msckf_b200_report rep;
+    marginalizeReport(rep);
+    checkNumeric(msckf_b200_fetch(engine_, &rep), "msckf_b200_fetch");
+    marginalizeAbsorb(rep);
+  }
+  // pieces of marginalize() for a caller that runs the device part of several filters as one batch (MSCKFBatch):
+  // Prepare packs the queued tracks (false: nothing queued), Report points a report at this filter's buffers, Absorb
+  // folds the fetched report back into the host bookkeeping (ref :368-372).
+  bool marginalizePrepare(msckf_b200_tracks& tr, bool in_engine_buffer) {
+    last_report_.clear();
+    launch_pending_ = false;
+    if (feature_tracks_to_residualize_.empty()) return false;
+    if (epoch_at_queue_ != epoch_)
+      throw std::logic_error("msckf_mono::MSCKF::marginalize: a measurement update was applied between update()/finish() and "
+                             "marginalize(); the queued tracks' clone snapshots (ref :250) would differ from the device state");
+    packTracks(feature_tracks_to_residualize_, nullptr, tr, in_engine_buffer);
+    return true;
+  }
+  void marginalizeReport(msckf_b200_report& rep) {
+    const int N = (int)feature_tracks_to_residualize_.size();
+    rp_cm_.resize(N); rp_tri_.resize(N); rp_valid_.resize(N); rp_acc_.resize(N); rp_gamma_.resize(N); rp_pfg_.resize(3 * (size_t)N);
+    rep.cm_ok = rp_cm_.data(); rep.tri_ok = rp_tri_.data(); rep.valid = rp_valid_.data(); rep.accepted = rp_acc_.data();
+    rep.gamma = rp_gamma_.data(); rep.p_f_G = rp_pfg_.data(); rep.m = 0; rep.rank = 0;
+  }
+  void marginalizeAbsorb(const msckf_b200_report& rep) {
     const int N = (int)feature_tracks_to_residualize_.size();
     last_report_.resize(N);
-    rp_cm_.resize(N); rp_tri_.resize(N); rp_valid_.resize(N); rp_acc_.resize(N); rp_gamma_.resize(N); rp_pfg_.resize(3 * (size_t)N);
-    msckf_b200_report rep;
-    rep.cm_ok = rp_cm_.data(); rep.tri_ok = rp_tri_.data(); rep.valid = rp_valid_.data(); rep.accepted = rp_acc_.data();
-    rep.gamma = rp_gamma_.data(); rep.p_f_G = rp_pfg_.data();
-    check(msckf_b200_fetch(engine_, &rep), "msckf_b200_fetch");
     for (int t = 0; t < N; ++t) {
       auto& track = feature_tracks_to_residualize_[t];
       TrackReport& r = last_report_[t];
       r.cm_ok = rp_cm_[t]; r.tri_ok = rp_tri_[t]; r.valid = rp_valid_[t]; r.accepted = rp_acc_[t]; r.gamma = rp_gamma_[t];
       for (int k = 0; k < 3; ++k) r.p_f_G(k) = rp_pfg_[3 * (size_t)t + k];
       r.rows = r.accepted ? (2 * (int)track.observations.size() - 3) : 0;
-      if (r.valid) { track.initialized = true; track.p_f_G = r.p_f_G; map_.push_back(r.p_f_G); }
+      if (r.valid) { track.initialized = true; track.p_f_G = r.p_f_G; map_.push_back(r.p_f_G); }  // ref :368-372
     }
     last_m_ = rep.m; last_rank_ = rep.rank;
     if (rep.m > 0) epoch_++;
@@ -448,53 +446,97 @@ class MSCKF {
   std::vector<featureTrackToResidualize<_S>> feature_tracks_to_residualize_;
   std::vector<size_t> tracks_to_remove_;
   size_t last_feature_id_ = 0;
-  imuState<_S> imu_state_;             // host mirror of the device state (refreshState)
-  std::vector<camState<_S>> cam_states_;  // bookkeeping on host; poses mirrored from the device
+  mutable imuState<_S> imu_state_;             // host mirror of the device state (refreshState)
+  mutable std::vector<camState<_S>> cam_states_;  // bookkeeping on host; poses mirrored from the device
   std::vector<camState<_S>> pruned_states_;
   aligned_vector<Vector3<_S>> map_;
   msckf_b200_engine* engine_ = nullptr;
   int device_ = 0, cap_clones_ = 0, cap_tracks_ = 0, cap_obs_ = 0;
-  bool state_dirty_ = false, launch_pending_ = false;
+  mutable bool state_dirty_ = false;
+  bool launch_pending_ = false;
+  mutable std::vector<_S> imu_queue_;  // IMU readings not yet handed to the device (7 scalars each)
   unsigned long long epoch_ = 0, epoch_at_queue_ = 0;
   std::vector<TrackReport> last_report_;
   int last_m_ = 0, last_rank_ = 0;
   std::vector<int> pk_off_, pk_idx_, rp_cm_, rp_tri_, rp_valid_, rp_acc_;
-  std::vector<_S> pk_obs_, rp_gamma_, rp_pfg_;
+  std::vector<_S> pk_obs_, pk_pfg_, rp_gamma_, rp_pfg_;
 
   static void check(int rc, const char* what) {
     if (rc != 0) throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + msckf_b200_last_error());
   }
+  // a non-finite update is not an error in the reference: its only anomaly handling is a print (ref :1405-1409)
+  static void checkNumeric(int rc, const char* what) {
+    if (rc == MSCKF_B200_ERR_NUMERIC) { std::cout << "[msckf_b200] " << what << ": " << msckf_b200_last_error() << std::endl; return; }
+    check(rc, what);
+  }
+  void moveFrom(MSCKF& o) {
+    camera_ = o.camera_; noise_params_ = o.noise_params_; msckf_params_ = o.msckf_params_;
+    feature_tracks_ = std::move(o.feature_tracks_); tracked_feature_ids_ = std::move(o.tracked_feature_ids_);
+    feature_tracks_to_residualize_ = std::move(o.feature_tracks_to_residualize_); tracks_to_remove_ = std::move(o.tracks_to_remove_);
+    last_feature_id_ = o.last_feature_id_; imu_state_ = o.imu_state_; cam_states_ = std::move(o.cam_states_);
+    pruned_states_ = std::move(o.pruned_states_); map_ = std::move(o.map_);
+    engine_ = o.engine_; o.engine_ = nullptr;
+    device_ = o.device_; cap_clones_ = o.cap_clones_; cap_tracks_ = o.cap_tracks_; cap_obs_ = o.cap_obs_;
+    state_dirty_ = o.state_dirty_; launch_pending_ = o.launch_pending_; imu_queue_ = std::move(o.imu_queue_);
+    epoch_ = o.epoch_; epoch_at_queue_ = o.epoch_at_queue_; last_report_ = std::move(o.last_report_);
+    last_m_ = o.last_m_; last_rank_ = o.last_rank_;
+  }
+  // the engine handle for a call that needs the device state: queued IMU readings are applied first
+  msckf_b200_engine* eng() const {
+    if (!imu_queue_.empty()) {
+      const int k = (int)(imu_queue_.size() / 7);
+      const int rc = msckf_b200_propagate_n(engine_, imu_queue_.data(), k);
+      imu_queue_.clear();
+      check(rc, "msckf_b200_propagate_n");
+    }
+    return engine_;
+  }
 
-  void packTracks(const std::vector<featureTrackToResidualize<_S>>& tracks) {
+  // Flat SoA form of a track batch.  in_engine_buffer: packed straight into the engine's pinned input block
+  // (msckf_b200_input_buffer: no second copy on the way to the device); otherwise into this object's own vectors.
+  // with_pfg: the tracks' positions ride along (RESIDUALIZE).
+  void packTracks(const std::vector<featureTrackToResidualize<_S>>& tracks, const std::vector<featureTrackToResidualize<_S>>* with_pfg,
+                  msckf_b200_tracks& tr, bool in_engine_buffer = true) {
     const size_t N = tracks.size();
-    pk_off_.resize(N + 1);
     size_t tot = 0;
-    for (size_t t = 0; t < N; ++t) { pk_off_[t] = (int)tot; tot += tracks[t].observations.size(); }
-    pk_off_[N] = (int)tot;
-    pk_obs_.resize(2 * tot);
-    pk_idx_.resize(tot);
+    for (size_t t = 0; t < N; ++t) tot += tracks[t].observations.size();
+    int* off; int* idx; _S* obs; _S* pfg = nullptr;
+    if (in_engine_buffer) {
+      check(msckf_b200_input_buffer(eng(), (int)N, (int)tot, &tr), "msckf_b200_input_buffer");
+      off = const_cast<int*>(tr.obs_offset); idx = const_cast<int*>(tr.clone_index);
+      obs = static_cast<_S*>(const_cast<void*>(tr.obs)); pfg = static_cast<_S*>(const_cast<void*>(tr.p_f_G));
+    } else {
+      pk_off_.resize(N + 1); pk_obs_.resize(2 * tot); pk_idx_.resize(tot); pk_pfg_.resize(3 * N);
+      off = pk_off_.data(); idx = pk_idx_.data(); obs = pk_obs_.data(); pfg = pk_pfg_.data();
+      tr.n_tracks = (int)N; tr.obs_offset = off; tr.obs = obs; tr.clone_index = idx; tr.p_f_G = pfg;
+    }
+    if (!with_pfg) tr.p_f_G = nullptr;
+    tot = 0;
+    for (size_t t = 0; t < N; ++t) { off[t] = (int)tot; tot += tracks[t].observations.size(); }
+    off[N] = (int)tot;
     for (size_t t = 0; t < N; ++t) {
-      const auto& tr = tracks[t];
-      if (tr.cam_state_indices.size() != tr.observations.size())
+      const auto& trk = tracks[t];
+      if (trk.cam_state_indices.size() != trk.observations.size())
         throw std::logic_error("track observations and clone indices differ in number");
       // the reference clears the queue in update() only (:218): finish() after a marginalize() would re-residualise the
       // last update's tracks with their old positional indices (undefined behaviour there once clones were pruned)
-      for (size_t ci : tr.cam_state_indices)
+      for (size_t ci : trk.cam_state_indices)
         if (ci >= cam_states_.size()) throw std::logic_error("stale residualisation queue: clone index out of range (reference: undefined behaviour)");
-      for (size_t i = 0; i < tr.observations.size(); ++i) {
-        pk_obs_[2 * (pk_off_[t] + i)] = tr.observations[i](0);
-        pk_obs_[2 * (pk_off_[t] + i) + 1] = tr.observations[i](1);
-        pk_idx_[pk_off_[t] + i] = (int)tr.cam_state_indices[i];
+      for (size_t i = 0; i < trk.observations.size(); ++i) {
+        obs[2 * (off[t] + i)] = trk.observations[i](0);
+        obs[2 * (off[t] + i) + 1] = trk.observations[i](1);
+        idx[off[t] + i] = (int)trk.cam_state_indices[i];
       }
+      if (with_pfg) for (int c = 0; c < 3; ++c) pfg[3 * t + c] = (*with_pfg)[t].p_f_G(c);
     }
   }
 
   // pull the IMU state and clone poses back from the device when something changed them
-  void refreshState() {
+  void refreshState() const {
     if (!state_dirty_ || !engine_) return;
     _S im[29];
     std::vector<_S> poses(7 * std::max<size_t>(cam_states_.size(), 1));
-    check(msckf_b200_get_state(engine_, im, poses.data()), "msckf_b200_get_state");
+    check(msckf_b200_get_state(eng(), im, poses.data()), "msckf_b200_get_state");
     for (int i = 0; i < 3; ++i) {
       imu_state_.p_I_G(i) = im[i]; imu_state_.v_I_G(i) = im[3 + i]; imu_state_.b_g(i) = im[6 + i]; imu_state_.b_a(i) = im[9 + i];
       imu_state_.g(i) = im[12 + i]; imu_state_.p_I_G_null(i) = im[19 + i]; imu_state_.v_I_G_null(i) = im[22 + i];
@@ -555,6 +597,51 @@ class MSCKF {
     if (rm_cam_state_ids.size() < 2) rm_cam_state_ids.clear();
     std::sort(rm_cam_state_ids.begin(), rm_cam_state_ids.end());
   }
+};
+
+// Not in the reference: marginalize() on several independent filters (sequences, Monte-Carlo trials) as ONE device batch --
+// one launch per kernel with the filter index in blockIdx.z, one CUDA graph, one packed copy each way
+// (msckf_b200_batch_* in include/msckf_b200.h).  Results are bit-identical to calling marginalize() on each filter.
+// While the object lives the filters share its CUDA stream; all their other member functions stay usable.
+template <typename _S>
+class MSCKFBatch {
+ public:
+  explicit MSCKFBatch(const std::vector<MSCKF<_S>*>& filters, int host_threads = 1) : filters_(filters), threads_(host_threads) {
+    std::vector<msckf_b200_engine*> es;
+    for (auto* f : filters_) es.push_back(f->engine());
+    if (msckf_b200_batch_create(es.data(), (int)es.size(), &batch_) != 0)
+      throw std::runtime_error(std::string("msckf_b200_batch_create failed: ") + msckf_b200_last_error());
+  }
+  ~MSCKFBatch() { if (batch_) msckf_b200_batch_destroy(batch_); }
+  MSCKFBatch(const MSCKFBatch&) = delete;
+  MSCKFBatch& operator=(const MSCKFBatch&) = delete;
+  void marginalize() {
+    const size_t n = filters_.size();
+    tracks_.assign(n, msckf_b200_tracks());
+    reports_.assign(n, msckf_b200_report());
+    active_.assign(n, 0);
+    bool any = false;
+    for (size_t i = 0; i < n; ++i) {
+      filters_[i]->engine();  // hand queued IMU readings over before the batch runs
+      active_[i] = filters_[i]->marginalizePrepare(tracks_[i], false) ? 1 : 0;
+      if (active_[i]) { filters_[i]->marginalizeReport(reports_[i]); any = true; } else tracks_[i].n_tracks = 0;
+    }
+    if (!any) return;
+    const int rc = msckf_b200_batch_update(batch_, MSCKF_B200_MARGINALIZE, tracks_.data(), reports_.data(), threads_);
+    if (rc == MSCKF_B200_ERR_NUMERIC) std::cout << "[msckf_b200] batch update: " << msckf_b200_last_error() << std::endl;
+    else if (rc != 0) throw std::runtime_error(std::string("msckf_b200_batch_update failed: ") + msckf_b200_last_error());
+    for (size_t i = 0; i < n; ++i)
+      if (active_[i]) filters_[i]->marginalizeAbsorb(reports_[i]);
+  }
+  msckf_b200_batch* handle() { return batch_; }
+
+ private:
+  std::vector<MSCKF<_S>*> filters_;
+  std::vector<msckf_b200_tracks> tracks_;
+  std::vector<msckf_b200_report> reports_;
+  std::vector<char> active_;
+  msckf_b200_batch* batch_ = nullptr;
+  int threads_ = 1;
 };
 
 }  // namespace msckf_mono

@@ -21,67 +21,48 @@
 #include <Eigen/Geometry>
 #include <Eigen/StdVector>
 namespace msckf_mono {
+// reference types.h:8-46, name for name
 template <typename _Scalar> using Quaternion = Eigen::Quaternion<_Scalar>;
 template <typename _Scalar> using Matrix3 = Eigen::Matrix<_Scalar, 3, 3>;
+template <typename _Scalar> using Matrix4 = Eigen::Matrix<_Scalar, 4, 4>;
+template <typename _Scalar> using MatrixX = Eigen::Matrix<_Scalar, Eigen::Dynamic, Eigen::Dynamic>;
+template <typename _Scalar> using RowVector3 = Eigen::Matrix<_Scalar, 1, 3>;
 template <typename _Scalar> using Vector2 = Eigen::Matrix<_Scalar, 2, 1>;
 template <typename _Scalar> using Vector3 = Eigen::Matrix<_Scalar, 3, 1>;
+template <typename _Scalar> using Vector4 = Eigen::Matrix<_Scalar, 4, 1>;
+template <typename _Scalar> using VectorX = Eigen::Matrix<_Scalar, Eigen::Dynamic, 1>;
 template <typename _Scalar> using Point = Vector3<_Scalar>;
 template <typename _Scalar> using GyroscopeReading = Vector3<_Scalar>;
 template <typename _Scalar> using AccelerometerReading = Vector3<_Scalar>;
+template <typename _Scalar> using Isometry3 = Eigen::Transform<_Scalar, 3, Eigen::Isometry>;
+// not in the reference: helpers of this header
 template <typename _Scalar, int R, int C> using FixedMatrix = Eigen::Matrix<_Scalar, R, C>;
 template <typename T> using aligned_vector = std::vector<T, Eigen::aligned_allocator<T>>;
+using IndexVector = Eigen::VectorXi;  // matrix_utils.h:61,79
+constexpr int DynamicSize = Eigen::Dynamic;
 }  // namespace msckf_mono
 #define MSCKF_B200_ALIGNED_NEW EIGEN_MAKE_ALIGNED_OPERATOR_NEW
 #else
+#include <msckf_mono/pod_linalg.h>
 namespace msckf_mono {
-namespace pod {
-template <typename S, int N>
-struct Vec {
-  S d[N];
-  Vec() { for (int i = 0; i < N; ++i) d[i] = S(0); }
-  S& operator()(int i) { return d[i]; }
-  const S& operator()(int i) const { return d[i]; }
-  S& operator[](int i) { return d[i]; }
-  const S& operator[](int i) const { return d[i]; }
-  S& x() { return d[0]; }
-  S& y() { return d[1]; }
-  S& z() { return d[2]; }
-  const S& x() const { return d[0]; }
-  const S& y() const { return d[1]; }
-  const S& z() const { return d[2]; }
-};
-template <typename S, int R, int C>
-struct Mat {
-  S d[R * C];
-  Mat() { for (int i = 0; i < R * C; ++i) d[i] = S(0); }
-  S& operator()(int i, int j) { return d[i * C + j]; }
-  const S& operator()(int i, int j) const { return d[i * C + j]; }
-  void setZero() { for (int i = 0; i < R * C; ++i) d[i] = S(0); }
-};
-template <typename S>
-struct Quat {  // constructor order (w,x,y,z) like Eigen::Quaternion
-  S x_, y_, z_, w_;
-  Quat() : x_(0), y_(0), z_(0), w_(1) {}
-  Quat(S w, S x, S y, S z) : x_(x), y_(y), z_(z), w_(w) {}
-  S& x() { return x_; }
-  S& y() { return y_; }
-  S& z() { return z_; }
-  S& w() { return w_; }
-  const S& x() const { return x_; }
-  const S& y() const { return y_; }
-  const S& z() const { return z_; }
-  const S& w() const { return w_; }
-};
-}  // namespace pod
+// reference types.h:8-46, name for name, over the Eigen-free stand-ins of pod_linalg.h
 template <typename _Scalar> using Quaternion = pod::Quat<_Scalar>;
 template <typename _Scalar> using Matrix3 = pod::Mat<_Scalar, 3, 3>;
-template <typename _Scalar> using Vector2 = pod::Vec<_Scalar, 2>;
-template <typename _Scalar> using Vector3 = pod::Vec<_Scalar, 3>;
+template <typename _Scalar> using Matrix4 = pod::Mat<_Scalar, 4, 4>;
+template <typename _Scalar> using MatrixX = pod::Mat<_Scalar, pod::Dynamic, pod::Dynamic>;
+template <typename _Scalar> using RowVector3 = pod::Mat<_Scalar, 1, 3>;
+template <typename _Scalar> using Vector2 = pod::Mat<_Scalar, 2, 1>;
+template <typename _Scalar> using Vector3 = pod::Mat<_Scalar, 3, 1>;
+template <typename _Scalar> using Vector4 = pod::Mat<_Scalar, 4, 1>;
+template <typename _Scalar> using VectorX = pod::Mat<_Scalar, pod::Dynamic, 1>;
 template <typename _Scalar> using Point = Vector3<_Scalar>;
 template <typename _Scalar> using GyroscopeReading = Vector3<_Scalar>;
 template <typename _Scalar> using AccelerometerReading = Vector3<_Scalar>;
+template <typename _Scalar> using Isometry3 = pod::Iso3<_Scalar>;
 template <typename _Scalar, int R, int C> using FixedMatrix = pod::Mat<_Scalar, R, C>;
 template <typename T> using aligned_vector = std::vector<T>;
+using IndexVector = pod::Mat<int, pod::Dynamic, 1>;
+constexpr int DynamicSize = pod::Dynamic;
 }  // namespace msckf_mono
 #define MSCKF_B200_ALIGNED_NEW
 #endif
@@ -137,12 +118,14 @@ struct MSCKFParams {
   _Scalar redundancy_angle_thresh, redundancy_distance_thresh;
   int min_track_length, max_track_length, max_cam_states;
 };
-// types.h:102-113.  The reference stores copies of the observing clones; here the clones are device
-// resident and a residualised track carries their POSITIONS in the window (cam_state_indices, msckf.h:1481).
+// types.h:102-113.  The reference stores copies of the observing clones in `cam_states`; here the clones are
+// device resident and a residualised track carries their POSITIONS in the window (cam_state_indices,
+// msckf.h:1481).  The member is kept for source compatibility; the drop-in class leaves it empty.
 template <typename _Scalar>
 struct featureTrackToResidualize {
   size_t feature_id;
   aligned_vector<Vector2<_Scalar>> observations;
+  std::vector<camState<_Scalar>> cam_states;
   std::vector<size_t> cam_state_indices;
   bool initialized;
   Vector3<_Scalar> p_f_G;

@@ -47,8 +47,14 @@ int msckf_mono_pack_queued(void* h, int* obs_offset, double* obs, int* clone_ind
 /* pipelining helpers: marginalize() = launch + collect */
 int msckf_mono_marginalize_launch(void* h);
 int msckf_mono_marginalize_collect(void* h);
-/* marginalize() on n independent filters: launch on all, then collect on all, the host work of the filters spread over
- * `threads` host threads (each filter has its own stream: the updates overlap on the GPU) */
+/* marginalize() on n independent filters of one scalar type as ONE device batch (msckf_mono::MSCKFBatch<_S>: one launch per
+ * kernel with the filter index in blockIdx.z, one CUDA graph, one packed copy each way); `threads` host threads share the
+ * packing.  Bit-identical to marginalize() on each filter.  _batch_create makes the batch persistent (the filters share its
+ * stream while it lives); msckf_mono_marginalize_batch is the one-shot form (temporary batch around one call). */
+int msckf_mono_batch_create(void** handles, int n, int threads, void** out);
+void msckf_mono_batch_destroy(void* batch);
+int msckf_mono_batch_marginalize(void* batch);
+void* msckf_mono_batch_handle(void* batch); /* the msckf_b200_batch* beneath */
 int msckf_mono_marginalize_batch(void** handles, int n, int threads);
 /* the msckf_b200_engine* beneath (for CUDA-event timing on its stream, launch counts, state copies) */
 void* msckf_mono_engine(void* h);

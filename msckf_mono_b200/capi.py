@@ -64,6 +64,79 @@ class TrackBatch:
         return self.off.nbytes + self.obs.nbytes + self.idx.nbytes + (0 if self.pfg is None else self.pfg.nbytes)
 
 
+class Batch:
+    """msckf_b200_batch: n engines whose updates run as ONE device batch (filter index in blockIdx.z, one CUDA graph, one
+    packed copy each way).  While it lives the engines share its stream."""
+
+    def __init__(self, engines):
+        self.engines = list(engines)
+        n = len(self.engines)
+        hs = (C.c_void_p * n)(*[e.h for e in self.engines])
+        self.h = C.c_void_p()
+        check(lib().msckf_b200_batch_create(hs, C.c_int(n), C.byref(self.h)), "msckf_b200_batch_create")
+        lib().msckf_b200_batch_launch_count.restype = C.c_longlong
+
+    def close(self):
+        if self.h:
+            lib().msckf_b200_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _tracks(self, batches):
+        assert len(batches) == len(self.engines)
+        return (Tracks * len(batches))(*[b.c for b in batches])
+
+    def stage(self, mode, batches, threads=1):
+        self._keep = batches
+        check(lib().msckf_b200_batch_stage(self.h, C.c_int(mode), self._tracks(batches), C.c_int(threads)), "msckf_b200_batch_stage")
+
+    def launch(self):
+        check(lib().msckf_b200_batch_launch(self.h), "msckf_b200_batch_launch")
+
+    def launch_timed(self):
+        ms = C.c_float()
+        check(lib().msckf_b200_batch_launch_timed(self.h, C.byref(ms)), "msckf_b200_batch_launch_timed")
+        return ms.value
+
+    def fetch(self, batches=None):
+        batches = batches or self._keep
+        n = len(self.engines)
+        reps = (Report * n)()
+        accs = []
+        for i, b in enumerate(batches):
+            acc = np.zeros(max(b.n_tracks, 1), dtype=np.int32)
+            reps[i].accepted = acc.ctypes.data_as(C.POINTER(C.c_int))
+            accs.append(acc)
+        check(lib().msckf_b200_batch_fetch(self.h, reps), "msckf_b200_batch_fetch")
+        return [{"m": reps[i].m, "rank": reps[i].rank, "accepted": accs[i][:batches[i].n_tracks]} for i in range(n)]
+
+    def update(self, mode, batches, threads=1):
+        """host buffers in, reports out: packing + one H2D + kernels + one D2H (the batch's end-to-end call)."""
+        n = len(self.engines)
+        reps = (Report * n)()
+        accs = []
+        for i, b in enumerate(batches):
+            acc = np.zeros(max(b.n_tracks, 1), dtype=np.int32)
+            reps[i].accepted = acc.ctypes.data_as(C.POINTER(C.c_int))
+            accs.append(acc)
+        check(lib().msckf_b200_batch_update(self.h, C.c_int(mode), self._tracks(batches), reps, C.c_int(threads)), "msckf_b200_batch_update")
+        return [{"m": reps[i].m, "rank": reps[i].rank, "accepted": accs[i][:batches[i].n_tracks]} for i in range(n)]
+
+    def kernel_times(self):
+        ms = (C.c_float * 32)()
+        names = (C.c_char_p * 32)()
+        n = check(lib().msckf_b200_batch_kernel_times(self.h, ms, names, C.c_int(32)), "msckf_b200_batch_kernel_times")
+        return [(names[i].decode(), ms[i]) for i in range(n)]
+
+    def launch_count(self):
+        return int(lib().msckf_b200_batch_launch_count(self.h))
+
+
 def update_batch(engines, mode, batches, threads=8):
     """msckf_b200_update_batch: one update per engine (independent filters), host work on `threads` threads.
     Returns the per-engine (m, rank, accepted) reports."""
@@ -128,6 +201,24 @@ class Engine:
 
     def synchronize(self):
         check(lib().msckf_b200_synchronize(self.h), "msckf_b200_synchronize")
+
+    def propagate_n(self, readings):
+        r = np.ascontiguousarray(readings, dtype=self.dtype).reshape(-1, 7)
+        check(lib().msckf_b200_propagate_n(self.h, r.ctypes.data_as(C.c_void_p), C.c_int(len(r))), "msckf_b200_propagate_n")
+
+    def augment(self):
+        check(lib().msckf_b200_augment(self.h), "msckf_b200_augment")
+
+    def prune(self, keep):
+        k = np.ascontiguousarray(keep, dtype=np.int32)
+        check(lib().msckf_b200_prune(self.h, k.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(len(k))), "msckf_b200_prune")
+
+    def update(self, mode, batch):
+        rep = Report()
+        acc = np.zeros(max(batch.n_tracks, 1), dtype=np.int32)
+        rep.accepted = acc.ctypes.data_as(C.POINTER(C.c_int))
+        check(lib().msckf_b200_update(self.h, C.c_int(mode), C.byref(batch.c), C.byref(rep)), "msckf_b200_update")
+        return {"m": rep.m, "rank": rep.rank, "accepted": acc[:batch.n_tracks]}
 
     def set_option(self, key, value):
         check(lib().msckf_b200_set_option(self.h, C.c_int(key), C.c_double(value)), "msckf_b200_set_option")

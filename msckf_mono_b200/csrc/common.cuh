@@ -25,6 +25,64 @@ struct DevState {
   double last_dx_norm;
 };
 
+// Everything one measurement update of one filter needs on the device: sizes, the packed input / report blocks, the
+// filter's resident state and its workspaces.  One UpdArgs per filter lives at the head of the packed input block
+// (engine.cu), so that a kernel launch only carries a pointer to an ARRAY of them and the filter index in blockIdx.z:
+// the same launch (and the same captured CUDA graph) serves one filter or a whole batch of independent filters, and
+// buffer swaps (prune) or re-allocations never invalidate a captured graph.
+template <class S>
+struct UpdArgs {
+  int n_tracks, M, Lmax, ldp;
+  int ld, n, mode, has_yf;   // has_yf: k_jac's shared memory includes the single-warp gate Cholesky's copy
+  int K, nsplit, kchunk, tail_kind;
+  double rank_thr;
+  // packed input block
+  const int* obs_off;    // [N+1]
+  const S* obs;          // [sumL*2] normalised image coordinates
+  const int* clone_idx;  // [sumL] positional index of the observing clone
+  const S* pfg_given;    // optional [N*3]: residualize tracks at given positions (pruneRedundantStates)
+  // resident filter state
+  S* poses;              // [M*8] current clone poses (q xyzw, p, pad)
+  S* P;                  // [n x n], leading dim ldp
+  DevState<S>* st;
+  // packed report block
+  int* m_out;            // total number of stacked rows m
+  int* rank_out;
+  int* cm_eff;           // [N] "not rejected by checkMotion" (msckf.h:354) as reported to the host
+  int* cm_ok;            // [N] checkMotion result
+  int* tri_ok;           // [N] initializePosition validity
+  int* valid;            // [N]
+  int* accept;           // [N]
+  S* pfg;                // [N*3]
+  S* gamma;              // [N]
+  // workspaces
+  unsigned long long* counter_snap;  // num_feature_tracks_residualized_ before this batch (read by k_jac)
+  int* src;              // [N] index of the track whose p_f_G loop B uses (msckf.h:419)
+  int* rows;             // [N] rho_j = 2L-3
+  int* row_off;          // [N+1] ordered stacking (msckf.h:433-445)
+  unsigned* done;        // CTA ticket counter of k_jac (zero between launches)
+  S* Xg;                 // [sumL*12] H_x blocks (2x6 per observation)
+  S* rg;                 // [sumL*2]  residuals
+  S* Vg;                 // [sumL*2*3] Householder vectors of the null-space projection
+  S* taug;               // [N*3]
+  double* Z;             // [3N x c]  U_j^T X_j scattered to clone columns
+  double* Yq;            // [3N x c]  U_j^T D X_j - 1/2 (U_j^T D U_j) Z_j
+  double* ur;            // [3N]      U_j^T r_j
+  double *G1p, *G2p;     // split-K partials of the Gram products
+  double *D1, *D2, *bb;  // per-clone 6x6 sums
+  double *T2, *R2, *r2, *TP, *S2, *W, *G, *y, *dx, *idiag;
+  int* keep;
+  unsigned long long* prof;  // optional: %globaltimer stamps (profiling aid)
+};
+
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor grid has completed
+// and its writes are visible.  EVERY kernel of the update calls it first, in every CTA, before any early return -- a grid
+// that finished without waiting would release ITS dependent too early.  pdl_launch() lets the next kernel's CTAs be
+// scheduled (they park in their own pdl_wait()).  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -11,43 +11,6 @@
 
 namespace mb {
 
-template <class S>
-struct FeatArgs {
-  int n_tracks, M, Lmax, ldp;
-  int has_yf;  // k_jac's shared memory includes the single-warp gate Cholesky's copy (dropped at the longest fp64 tracks)
-  const int* obs_off;    // [N+1]
-  const S* obs;          // [sumL*2] normalised image coordinates
-  const int* clone_idx;  // [sumL] positional index of the observing clone
-  const S* poses;        // [M*8] current clone poses (q xyzw, p, pad)
-  const S* P;            // [n x n], leading dim ldp, prior covariance
-  const DevState<S>* st;
-  // k_tri out
-  S* pfg;       // [N*3]
-  unsigned long long* counter_snap;  // num_feature_tracks_residualized_ before this batch (read by k_jac)
-  int* cm_eff;  // [N] "not rejected by checkMotion" (msckf.h:354) as reported to the host
-  int* cm_ok;   // [N] checkMotion result
-  int* tri_ok;  // [N] initializePosition validity
-  // loop-A bookkeeping out (k_jac prologue)
-  int* valid;  // [N]
-  int* src;    // [N] index of the track whose p_f_G loop B uses (msckf.h:419)
-  // k_jac out
-  const S* pfg_given;  // optional [N*3]: residualize tracks at given positions (pruneRedundantStates)
-  int* accept;         // [N]
-  S* gamma;            // [N]
-  int* rows;           // [N] rho_j = 2L-3
-  int* row_off;        // [N+1] ordered stacking (msckf.h:433-445): exclusive prefix sum of rows, by the last CTA of k_jac
-  int* m_out;          // total number of stacked rows m
-  unsigned* done;      // CTA ticket counter of k_jac (zero between launches)
-  S* Xg;               // [sumL*12] H_x blocks (2x6 per observation)
-  S* rg;               // [sumL*2]  residuals
-  S* Vg;               // [sumL*2*3] Householder vectors of the null-space projection (unit lower trapezoid)
-  S* taug;             // [N*3]
-  unsigned long long* prof;  // optional: %globaltimer stamps of CTA 0's phases (profiling aid)
-  double* Z;           // [3N x c]  U_j^T X_j scattered to clone columns
-  double* Yq;          // [3N x c]  U_j^T D X_j - 1/2 (U_j^T D U_j) Z_j
-  double* ur;          // [3N]      U_j^T r_j
-};
-
 // Eigen::LDLT (diagonal pivoting) solve of a symmetric 3x3 system, msckf.h:1222, register-only.
 // Eigen's unblocked LDLT is left-looking: at step k it picks the largest |diagonal| among the not yet eliminated
 // (and not yet updated) entries, i.e. the elimination order is the descending order of the ORIGINAL |a_ii|
@@ -121,7 +84,11 @@ __device__ __forceinline__ S track_cost(const S* rel, const S* z, int L, int lan
 }
 
 template <class S, int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_tri(FeatArgs<S> a) {
+__global__ void __launch_bounds__(WPB * 32) k_tri(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  const UpdArgs<S>& a = args[blockIdx.z];
+  if ((int)blockIdx.x * WPB >= a.n_tracks) return;  // (a batch launch is sized for its largest filter)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   S* poses = reinterpret_cast<S*>(smem_raw + 16);
@@ -138,6 +105,11 @@ __global__ void __launch_bounds__(WPB * 32) k_tri(FeatArgs<S> a) {
   for (int e = lane; e < 2 * L; e += 32) z[e] = zg[e];
   __syncwarp();
   if (blockIdx.x == 0 && threadIdx.x == 0) *a.counter_snap = a.st->num_residualized;
+  if (L < 2) {  // a single observation cannot be triangulated (the reference's checkMotion is false there, msckf.h:982-984,
+                // and its initial guess divides by zero): reported as rejected instead of failing the batch
+    if (lane == 0) { a.pfg[3 * t] = a.pfg[3 * t + 1] = a.pfg[3 * t + 2] = S(0); a.cm_ok[t] = 0; a.tri_ok[t] = 0; }
+    return;
+  }
   // first clone: camera -> world
   const S* pose0 = poses + kPoseStride * idx[0];
   S C0[9];
@@ -383,12 +355,12 @@ __host__ __device__ inline size_t jac_smem_bytes(int L, int M, bool with_yf = tr
 // Ordered stacking (msckf.h:433-445): the exclusive prefix sum of the accepted blocks' row counts, computed by whichever
 // CTA of k_jac finishes last (ticket counter) -- a separate 1-CTA kernel for 300 integers cost 8 us of launch latency.
 template <class S>
-__device__ __forceinline__ void jac_finish(const FeatArgs<S>& a) {
+__device__ __forceinline__ void jac_finish(const UpdArgs<S>& a) {
   __shared__ int s_last;
   __shared__ int s_part[JT / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __syncthreads();
-  if (tid == 0) { __threadfence(); s_last = (atomicAdd(a.done, 1u) == gridDim.x - 1) ? 1 : 0; }
+  if (tid == 0) { __threadfence(); s_last = (atomicAdd(a.done, 1u) == (unsigned)a.n_tracks - 1u) ? 1 : 0; }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -404,7 +376,7 @@ __device__ __forceinline__ void jac_finish(const FeatArgs<S>& a) {
   int run = incl - sum;
   for (int w = 0; w < warp; ++w) run += s_part[w];
   for (int k = b; k < e; ++k) { a.row_off[k] = run; run += __ldcg(a.rows + k); }
-  if (tid == JT - 1) { a.row_off[N] = run; *a.m_out = run; }
+  if (tid == JT - 1) { a.row_off[N] = run; a.m_out[0] = run; a.m_out[2] = 0; /* status: set by k_syrk / k_inject */ }
   if (tid == 0) *a.done = 0u;
 }
 
@@ -412,7 +384,12 @@ __device__ __forceinline__ void jac_finish(const FeatArgs<S>& a) {
 // (msckf.h:352-399: valid flags, num_feature_tracks_residualized_, and the p_f_G_vec index of :419) folded into
 // the prologue.  mode 0: marginalize semantics; mode 1: every track valid at its given position.
 template <class S>
-__global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, int mode) {
+__global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  const UpdArgs<S>& a = args[blockIdx.z];
+  if ((int)blockIdx.x >= a.n_tracks) return;
+  DevState<S>* st_rw = a.st;
+  const int mode = (a.mode == 2) ? 1 : 0;  // MSCKF_B200_RESIDUALIZE: every track valid at its given position
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   S* poses = reinterpret_cast<S*>(smem_raw + 16);
@@ -431,7 +408,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
     if (a.prof && blockIdx.x == 0 && threadIdx.x == 0 && prof_i < 30) {
       unsigned long long tt;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt));
-      a.prof[prof_i++] = tt;
+      a.prof[40 + prof_i++] = tt;
     }
   };
   stamp();
@@ -493,8 +470,8 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   }
   __syncthreads();
   stamp();  // bookkeeping
-  const int valid = s_valid, src = s_src;
   const int o0 = a.obs_off[t], L = a.obs_off[t + 1] - o0, L2 = 2 * L;
+  const int valid = (L >= 2) ? s_valid : 0, src = s_src;  // fewer than two observations: no null space (2L - 3 < 1)
   double* Zr = a.Z + (size_t)3 * t * c;
   double* Yr = a.Yq + (size_t)3 * t * c;
   if (tid == 0) { a.valid[t] = valid; a.src[t] = src; }
@@ -521,7 +498,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
   const S* z = a.obs + 2 * (size_t)o0;
   const DevState<S>* st = a.st;
   const S g[3] = {st->g[0], st->g[1], st->g[2]};
-  const S* pfsrc = a.pfg_given ? (a.pfg_given + 3 * t) : (a.pfg + 3 * src);
+  const S* pfsrc = mode ? (a.pfg_given + 3 * t) : (a.pfg + 3 * src);
   const S pf[3] = {pfsrc[0], pfsrc[1], pfsrc[2]};
   // ---- residual + measurement Jacobian blocks with the observability projection (msckf.h:915-950, 960-978)
   for (int i = tid; i < L; i += JT) {
@@ -921,7 +898,7 @@ __global__ void __launch_bounds__(JT) k_jac(FeatArgs<S> a, DevState<S>* st_rw, i
     for (int q = 0; q < 3; ++q) a.ur[3 * t + q] = acc ? urv[q] : 0.0;
   }
   stamp();  // outputs
-  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[prof_i] = 0ull;
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[40 + prof_i] = 0ull;
   jac_finish(a);
 }
 

@@ -39,6 +39,7 @@ struct Base {
   virtual int queued(uint64_t*, int*, int) = 0;
   virtual int pack_queued(int*, double*, int*, int, int) = 0;
   virtual msckf_b200_engine* engine() = 0;
+  virtual void* filter_ptr() = 0;
   virtual int last_m() = 0;
   virtual int last_rank() = 0;
   int dtype = 0;
@@ -172,6 +173,7 @@ struct Impl : Base {
     return (int)q.size();
   }
   msckf_b200_engine* engine() override { return f.engine(); }
+  void* filter_ptr() override { return &f; }
   int last_m() override { return f.lastStackedRows(); }
   int last_rank() override { return f.lastRank(); }
 };
@@ -208,24 +210,57 @@ int msckf_mono_add_features(void* h, const double* z, const uint64_t* ids, int n
 int msckf_mono_marginalize(void* h) { return guard([&] { H->marginalize(); return 0; }); }
 int msckf_mono_marginalize_launch(void* h) { return guard([&] { H->marginalize_launch(); return 0; }); }
 int msckf_mono_marginalize_collect(void* h) { return guard([&] { H->marginalize_collect(); return 0; }); }
-int msckf_mono_marginalize_batch(void** handles, int n, int threads) {
+// a persistent device batch over n filters of one scalar type (msckf_mono::MSCKFBatch<_S>)
+struct ViewBatch {
+  int dtype = 0;
+  MSCKFBatch<float>* bf = nullptr;
+  MSCKFBatch<double>* bd = nullptr;
+  ~ViewBatch() { delete bf; delete bd; }
+};
+int msckf_mono_batch_create(void** handles, int n, int threads, void** out) {
   return guard([&] {
-    if (n <= 0) return 0;
-    const int T = std::max(1, std::min(threads, n));
-    std::vector<std::string> err(T);
-    auto work = [&](int w) {
-      try {
-        for (int i = w; i < n; i += T) static_cast<Base*>(handles[i])->marginalize_launch();
-        for (int i = w; i < n; i += T) static_cast<Base*>(handles[i])->marginalize_collect();
-      } catch (const std::exception& e) { err[w] = e.what(); if (err[w].empty()) err[w] = "error"; }
-    };
-    std::vector<std::thread> pool;
-    for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
-    work(0);
-    for (auto& t : pool) t.join();
-    for (const auto& e : err) if (!e.empty()) throw std::runtime_error(e);
+    if (n <= 0 || !handles || !out) throw std::runtime_error("batch_create: bad arguments");
+    const int dtype = static_cast<Base*>(handles[0])->dtype;
+    auto* vb = new ViewBatch();
+    vb->dtype = dtype;
+    try {
+      if (dtype == 0) {
+        std::vector<MSCKF<float>*> fs;
+        for (int i = 0; i < n; ++i) { Base* b = static_cast<Base*>(handles[i]); if (b->dtype != dtype) throw std::runtime_error("batch_create: mixed scalar types"); fs.push_back(static_cast<MSCKF<float>*>(b->filter_ptr())); }
+        vb->bf = new MSCKFBatch<float>(fs, threads);
+      } else {
+        std::vector<MSCKF<double>*> fs;
+        for (int i = 0; i < n; ++i) { Base* b = static_cast<Base*>(handles[i]); if (b->dtype != dtype) throw std::runtime_error("batch_create: mixed scalar types"); fs.push_back(static_cast<MSCKF<double>*>(b->filter_ptr())); }
+        vb->bd = new MSCKFBatch<double>(fs, threads);
+      }
+    } catch (...) { delete vb; throw; }
+    *out = vb;
     return 0;
   });
+}
+void msckf_mono_batch_destroy(void* b) { delete static_cast<ViewBatch*>(b); }
+int msckf_mono_batch_marginalize(void* b) {
+  return guard([&] {
+    auto* vb = static_cast<ViewBatch*>(b);
+    if (vb->bf) vb->bf->marginalize(); else vb->bd->marginalize();
+    return 0;
+  });
+}
+void* msckf_mono_batch_handle(void* b) {
+  auto* vb = static_cast<ViewBatch*>(b);
+  return vb->bf ? (void*)vb->bf->handle() : (void*)vb->bd->handle();
+}
+// one-shot form: a temporary batch around one marginalize() of every filter
+int msckf_mono_marginalize_batch(void** handles, int n, int threads) {
+  if (n <= 0) return 0;
+  void* b = nullptr;
+  int rc = msckf_mono_batch_create(handles, n, threads, &b);
+  if (rc != 0) return rc;
+  rc = msckf_mono_batch_marginalize(b);
+  const std::string keep = g_err;
+  msckf_mono_batch_destroy(b);
+  g_err = keep;
+  return rc;
 }
 int msckf_mono_prune_redundant_states(void* h) { return guard([&] { H->prune_redundant(); return 0; }); }
 int msckf_mono_prune_empty_states(void* h) { return guard([&] { H->prune_empty(); return 0; }); }

@@ -24,11 +24,20 @@ constexpr int GT = 32;   // output tile
 constexpr int GK = 16;   // k-step
 
 // Partial Gram products over a K-split: G1p[s] = Z^T Z, G2p[s] = Z^T Yq + Yq^T Z, upper tiles only.
-__global__ void __launch_bounds__(256) k_gram(const double* __restrict__ Z, const double* __restrict__ Yq, int K, int c,
-                                             int kchunk, double* __restrict__ G1p, double* __restrict__ G2p) {
+template <class S>
+__global__ void __launch_bounds__(256) k_gram(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  const UpdArgs<S>& A = args[blockIdx.z];
+  const int K = A.K, c = A.n - kImuDim, kchunk = A.kchunk;
+  const double* __restrict__ Z = A.Z;
+  const double* __restrict__ Yq = A.Yq;
+  double* __restrict__ G1p = A.G1p;
+  double* __restrict__ G2p = A.G2p;
   __shared__ double sZa[GK][GT + 1], sZb[GK][GT + 1], sYa[GK][GT + 1], sYb[GK][GT + 1];
   // decode the (ta <= tb) tile pair
   const int ntile = (c + GT - 1) / GT;
+  if ((int)blockIdx.x >= ntile * (ntile + 1) / 2 || (int)blockIdx.y >= A.nsplit || A.n_tracks == 0) return;
   int pidx = blockIdx.x, ta = 0;
   while (pidx >= ntile - ta) { pidx -= ntile - ta; ++ta; }
   const int tb = ta + pidx;
@@ -72,11 +81,22 @@ __global__ void __launch_bounds__(256) k_gram(const double* __restrict__ Z, cons
 // Block-diagonal terms, one CTA per clone: D1 = sum X^T X, D2 = sum X^T D X (6x6), b = sum X^T r (6),
 // over the accepted tracks' observations of that clone.  Deterministic (fixed feature->thread map, tree reduce).
 template <class S>
-__global__ void __launch_bounds__(128) k_blockdiag(int N, const int* __restrict__ obs_off, const int* __restrict__ clone_idx,
-                                                  const int* __restrict__ accept, const S* __restrict__ Xg, const S* __restrict__ rg,
-                                                  double du, double dv, double* __restrict__ D1, double* __restrict__ D2,
-                                                  double* __restrict__ bb) {
+__global__ void __launch_bounds__(128) k_blockdiag(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  const UpdArgs<S>& A = args[blockIdx.z];
   const int clone = blockIdx.x;
+  if (clone >= A.M || A.n_tracks == 0) return;
+  const int N = A.n_tracks;
+  const int* __restrict__ obs_off = A.obs_off;
+  const int* __restrict__ clone_idx = A.clone_idx;
+  const int* __restrict__ accept = A.accept;
+  const S* __restrict__ Xg = A.Xg;
+  const S* __restrict__ rg = A.rg;
+  const double du = (double)A.st->u_var, dv = (double)A.st->v_var;
+  double* __restrict__ D1 = A.D1;
+  double* __restrict__ D2 = A.D2;
+  double* __restrict__ bb = A.bb;
   double acc[78];
 #pragma unroll
   for (int k = 0; k < 78; ++k) acc[k] = 0.0;
@@ -118,11 +138,24 @@ __global__ void __launch_bounds__(128) k_blockdiag(int N, const int* __restrict_
 }
 
 // Assemble T'' (n x n), r'' (n), R'' (n x n) except the <=15 head rows (k_head fills those afterwards).
-__global__ void __launch_bounds__(256) k_assemble(int n, int ld, int K, int nsplit, const double* __restrict__ G1p,
-                                                 const double* __restrict__ G2p, const double* __restrict__ D1,
-                                                 const double* __restrict__ D2, const double* __restrict__ bb,
-                                                 const double* __restrict__ Z, const double* __restrict__ ur, const int* __restrict__ m_in,
-                                                 double* __restrict__ T2, double* __restrict__ R2, double* __restrict__ r2) {
+template <class S>
+__global__ void __launch_bounds__(256) k_assemble(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  const UpdArgs<S>& A = args[blockIdx.z];
+  if (A.n_tracks == 0) return;
+  const int n = A.n, ld = A.ld, K = A.K, nsplit = A.nsplit;
+  const double* __restrict__ G1p = A.G1p;
+  const double* __restrict__ G2p = A.G2p;
+  const double* __restrict__ D1 = A.D1;
+  const double* __restrict__ D2 = A.D2;
+  const double* __restrict__ bb = A.bb;
+  const double* __restrict__ Z = A.Z;
+  const double* __restrict__ ur = A.ur;
+  const int* __restrict__ m_in = A.m_out;
+  double* __restrict__ T2 = A.T2;
+  double* __restrict__ R2 = A.R2;
+  double* __restrict__ r2 = A.r2;
   const int c = n - kImuDim;
   const bool full = *m_in <= n;  // m <= n: plain uncompressed update, all rows explicit (k_rows), no Gram part
   const size_t total = (size_t)n * n;
@@ -175,13 +208,28 @@ __global__ void __launch_bounds__(256) k_assemble(int n, int ld, int K, int nspl
 // Row t of feature j is A_j(:,t)^T [X_j | r_j] with A_j(:,t) = Q e_{3+t},  Q = H0 H1 H2 = I - V T V^T (compact WY,
 // exact reflectors tau_k = 2 / v_k^T v_k in fp64): every entry of Q costs O(1) from V (2L x 3) and T (3 x 3).
 template <class S>
-__global__ void __launch_bounds__(128) k_rows(int N, int n, int ld, const int* __restrict__ obs_off, const int* __restrict__ clone_idx,
-                                             const int* __restrict__ accept, const int* __restrict__ row_off, const int* __restrict__ m_in,
-                                             const S* __restrict__ Xg, const S* __restrict__ rg, const S* __restrict__ Vg,
-                                             const S* __restrict__ taug, const double* __restrict__ Z, double du, double dv,
-                                             double* __restrict__ T2, double* __restrict__ R2, double* __restrict__ r2) {
+__global__ void __launch_bounds__(128) k_rows(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  const UpdArgs<S>& A = args[blockIdx.z];
   extern __shared__ double sh[];  // V[2L][3] | W[2L][3]
   const int j = blockIdx.x;
+  if (j >= A.n_tracks) return;
+  const int n = A.n, ld = A.ld;
+  const int* __restrict__ obs_off = A.obs_off;
+  const int* __restrict__ clone_idx = A.clone_idx;
+  const int* __restrict__ accept = A.accept;
+  const int* __restrict__ row_off = A.row_off;
+  const int* __restrict__ m_in = A.m_out;
+  const S* __restrict__ Xg = A.Xg;
+  const S* __restrict__ rg = A.rg;
+  const S* __restrict__ Vg = A.Vg;
+  const S* __restrict__ taug = A.taug;
+  const double* __restrict__ Z = A.Z;
+  const double du = (double)A.st->u_var, dv = (double)A.st->v_var;
+  double* __restrict__ T2 = A.T2;
+  double* __restrict__ R2 = A.R2;
+  double* __restrict__ r2 = A.r2;
   if (!accept[j]) return;
   const int m = *m_in;
   const bool full = m <= n;

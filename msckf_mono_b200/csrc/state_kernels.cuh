@@ -71,9 +71,23 @@ __device__ __forceinline__ void lin15(S* C, int nterm, const double* coef, const
   __syncthreads();
 }
 
+// Up to kPropMax IMU readings per launch (msckf_b200_propagate_n: the shim queues the readings between two images), passed
+// by value so that the call needs no staging buffer and stays asynchronous.  The readings are applied one after the other
+// with exactly the arithmetic of a single propagate() each.
+constexpr int kPropMax = 16;
 template <class S>
-__global__ void __launch_bounds__(256) k_propagate(DevState<S>* st, S* __restrict__ P, int ldp, int M, S wx, S wy, S wz, S ax, S ay,
-                                                  S az, S dT) {
+struct PropBatch {
+  DevState<S>* st;
+  S* P;
+  int ldp, M, k, pad_;
+  S r[kPropMax][7];  // omega[3], a[3], dT
+};
+
+template <class S>
+__global__ void __launch_bounds__(256) k_propagate(const PropBatch<S> pb) {
+  DevState<S>* st = pb.st;
+  S* __restrict__ P = pb.P;
+  const int ldp = pb.ldp, M = pb.M;
   __shared__ S F[225], Phi[225], A2[225], A4[225], A6[225], A8[225], Um[225], Vm[225], Tm[225], Id[225];
   __shared__ S G[15 * 12], GQ[15 * 12];
   __shared__ S CT[9];            // C_IG^T
@@ -81,6 +95,9 @@ __global__ void __launch_bounds__(256) k_propagate(DevState<S>* st, S* __restric
   __shared__ int s_deg, s_sq;
   __shared__ S colsum[15];
   const int t = threadIdx.x;
+  for (int ir = 0; ir < pb.k; ++ir) {
+  const S wx = pb.r[ir][0], wy = pb.r[ir][1], wz = pb.r[ir][2], ax = pb.r[ir][3], ay = pb.r[ir][4], az = pb.r[ir][5], dT = pb.r[ir][6];
+  __syncthreads();
   if (t < 225) { F[t] = S(0); Id[t] = ((t / 15) == (t % 15)) ? S(1) : S(0); }
   if (t < 180) G[t] = S(0);
   __syncthreads();
@@ -350,6 +367,8 @@ __global__ void __launch_bounds__(256) k_propagate(DevState<S>* st, S* __restric
       st->p_I_G[i] = prop_p[i]; st->p_I_G_null[i] = prop_p[i];
     }
   }
+  __syncthreads();  // the next reading starts from the state and covariance written above
+  }
 }
 
 // augmentState (msckf.h:148-212): clone the IMU pose through the extrinsics and append 6 rows/columns to P.
@@ -405,10 +424,15 @@ __global__ void __launch_bounds__(256) k_augment(DevState<S>* st, S* __restrict_
   }
 }
 
-// P_new = P_old(map, map) with map = [0..14, kept clone blocks]; poses gathered likewise.
+// P_new = P_old(map, map) with map = [0..14, kept clone blocks]; poses gathered likewise.  The keep list travels as a
+// kernel argument: prune() needs no staging copy and no synchronisation.
+constexpr int kMaxKeep = 192;
+struct KeepList { int n; int idx[kMaxKeep]; };
 template <class S>
-__global__ void __launch_bounds__(256) k_gather(int n_new, const int* __restrict__ keep_clones, int n_keep, const S* __restrict__ Pold,
+__global__ void __launch_bounds__(256) k_gather(int n_new, const KeepList kl, const S* __restrict__ Pold,
                                                S* __restrict__ Pnew, int ldp, const S* __restrict__ poses_old, S* __restrict__ poses_new) {
+  const int* keep_clones = kl.idx;
+  const int n_keep = kl.n;
   const size_t total = (size_t)n_new * n_new;
   for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
     const int a = (int)(e / n_new), b = (int)(e % n_new);

@@ -171,14 +171,27 @@ __device__ __forceinline__ void tc_substitute(int n, int ld, int C, int crank, i
 }
 
 template <class S, int NB>
-__global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, const double* __restrict__ T2, double* __restrict__ G,
-                                                      double* __restrict__ A, double* __restrict__ Lout, int* __restrict__ keep,
-                                                      double* __restrict__ idiag,
-                                                      double thr, int* __restrict__ rank_out, const int* __restrict__ m_in,
-                                                      const double* __restrict__ TP, const double* __restrict__ r2,
-                                                      double* __restrict__ Wm, double* __restrict__ yv, S* __restrict__ P, int ldp,
-                                                      DevState<S>* st, S* __restrict__ poses, double* __restrict__ dx_out,
-                                                      unsigned long long* __restrict__ prof /*optional phase timestamps*/) {
+__global__ void __launch_bounds__(kTailThreads) k_tail(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  const UpdArgs<S>& ua = args[blockIdx.z];
+  if (ua.n_tracks == 0 || ua.tail_kind != (NB == 32 ? 1 : 2)) return;  // (uniform over the cluster)
+  const int n = ua.n, ld = ua.ld;
+  const double* __restrict__ T2 = ua.T2;
+  double* __restrict__ G = ua.G;
+  double* __restrict__ A = ua.S2;
+  double* __restrict__ Lout = ua.R2;     // receives L (R'' is consumed by k_gemm_s)
+  int* __restrict__ keep = ua.keep;
+  double* __restrict__ idiag = ua.idiag;
+  const double thr = ua.rank_thr;
+  int* __restrict__ rank_out = ua.rank_out;
+  const int* __restrict__ m_in = ua.m_out;
+  const double* __restrict__ TP = ua.TP;
+  const double* __restrict__ r2 = ua.r2;
+  double* __restrict__ Wm = ua.W;
+  double* __restrict__ yv = ua.y;
+  double* __restrict__ dx_out = ua.dx;
+  unsigned long long* __restrict__ prof = ua.prof;  // optional phase timestamps
   static_assert(NB <= 32, "the diagonal block is factorised by one warp, one row per lane");
   cg::cluster_group cluster = cg::this_cluster();
   int prof_i = 0;
@@ -376,9 +389,18 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(int n, int ld, int M, con
 
 // dx = W^T y, then the state correction of msckf.h:1373-1391.  Single CTA.
 template <class S>
-__global__ void __launch_bounds__(1024) k_inject(int n, int ld, int M, const double* __restrict__ Wm, const double* __restrict__ yv,
-                                                DevState<S>* st, S* __restrict__ poses, double* __restrict__ dx_out,
-                                                const int* __restrict__ m_in, const int* __restrict__ rank_in) {
+__global__ void __launch_bounds__(1024) k_inject(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  const UpdArgs<S>& ua = args[blockIdx.z];
+  if (ua.n_tracks == 0) return;
+  const int n = ua.n, ld = ua.ld, M = ua.M;
+  const double* __restrict__ Wm = ua.W;
+  const double* __restrict__ yv = ua.y;
+  DevState<S>* st = ua.st;
+  S* __restrict__ poses = ua.poses;
+  double* __restrict__ dx_out = ua.dx;
+  const int* __restrict__ m_in = ua.m_out;
+  const int* __restrict__ rank_in = ua.rank_out;
   extern __shared__ double sdx[];
   const int tid = threadIdx.x;
   if (*m_in == 0) {  // nothing accepted: the reference returns before touching the state (msckf.h:401-403,:1328)
@@ -423,6 +445,8 @@ __global__ void __launch_bounds__(1024) k_inject(int n, int ld, int M, const dou
     double nn = 0.0;
     for (int a = 0; a < n; ++a) nn += sdx[a] * sdx[a];
     st->last_dx_norm = sqrt(nn);
+    if (!isfinite(nn)) ua.m_out[2] = 1;  // non-finite delta-x (k_syrk flags a non-finite covariance entry the same way)
+    st->last_status = ua.m_out[2];
   }
   for (int ci = tid; ci < M; ci += 1024) {
     S* ps = poses + kPoseStride * ci;

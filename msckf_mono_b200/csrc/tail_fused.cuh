@@ -184,13 +184,24 @@ __device__ __forceinline__ void tf_invert(const double* Lf, const double* inv, d
 }
 
 template <class S>
-__global__ void __launch_bounds__(kTailThreads) k_tail_fused(int n, int ld, double* __restrict__ G /*T'' on entry: patched into Gamma in place*/,
-                                                            double* __restrict__ A, double thr, int* __restrict__ rank_out,
-                                                            const int* __restrict__ m_in, const double* __restrict__ TP,
-                                                            const double* __restrict__ r2, double* __restrict__ Wm,
-                                                            double* __restrict__ yv, double* __restrict__ dx_out,
-                                                            double* __restrict__ scratch /*>= 64 * (34 + ldt) doubles*/,
-                                                            unsigned long long* __restrict__ prof /*optional phase timestamps*/) {
+__global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  const UpdArgs<S>& ua = args[blockIdx.z];
+  if (ua.n_tracks == 0 || ua.tail_kind != 0) return;  // (uniform over the cluster)
+  const int n = ua.n, ld = ua.ld;
+  double* __restrict__ G = ua.T2;        // T'' on entry: patched into Gamma in place
+  double* __restrict__ A = ua.S2;
+  const double thr = ua.rank_thr;
+  int* __restrict__ rank_out = ua.rank_out;
+  const int* __restrict__ m_in = ua.m_out;
+  const double* __restrict__ TP = ua.TP;
+  const double* __restrict__ r2 = ua.r2;
+  double* __restrict__ Wm = ua.W;
+  double* __restrict__ yv = ua.y;
+  double* __restrict__ dx_out = ua.dx;
+  double* __restrict__ scratch = ua.G;   // >= 64 * (34 + ldt) doubles
+  unsigned long long* __restrict__ prof = ua.prof;  // optional phase timestamps
   namespace cg = cooperative_groups;
   constexpr int NB = kFB, LD = kFLD;
   double* Lsc = scratch;                      // [2][32][34] inverses of the current diagonal blocks' factors (A, G)

@@ -81,8 +81,15 @@ __device__ __forceinline__ void gemm_tile32(int n, int k_begin, int a0, int b0, 
 
 // TP[a][b] = sum_k T2[a][k] * P[k][b]      (T2 columns < 15 are zero)
 template <class S>
-__global__ void __launch_bounds__(kGemmThreads) k_gemm_tp(int n, int ld, const double* __restrict__ T2, const S* __restrict__ P, int ldp,
-                                               double* __restrict__ TP) {
+__global__ void __launch_bounds__(kGemmThreads) k_gemm_tp(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  const UpdArgs<S>& A = args[blockIdx.z];
+  const int n = A.n, ld = A.ld, ldp = A.ldp;
+  if ((int)blockIdx.x * 32 >= n || (int)blockIdx.y * 32 >= n || A.n_tracks == 0) return;
+  const double* __restrict__ T2 = A.T2;
+  const S* __restrict__ P = A.P;
+  double* __restrict__ TP = A.TP;
   gemm_tile32(n, kImuDim, blockIdx.y * 32, blockIdx.x * 32,
               [&](int k, int a) { return T2[(size_t)a * ld + k]; },
               [&](int k, int b) { return (double)P[(size_t)k * ldp + b]; },
@@ -90,8 +97,17 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_tp(int n, int ld, const d
 }
 
 // S2[a][b] = sum_k TP[a][k] * T2[b][k] + R2[a][b]
-__global__ void __launch_bounds__(kGemmThreads) k_gemm_s(int n, int ld, const double* __restrict__ TP, const double* __restrict__ T2,
-                                              const double* __restrict__ R2, double* __restrict__ S2) {
+template <class S>
+__global__ void __launch_bounds__(kGemmThreads) k_gemm_s(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  const UpdArgs<S>& A = args[blockIdx.z];
+  const int n = A.n, ld = A.ld;
+  if ((int)blockIdx.x * 32 >= n || (int)blockIdx.y * 32 >= n || A.n_tracks == 0) return;
+  const double* __restrict__ TP = A.TP;
+  const double* __restrict__ T2 = A.T2;
+  const double* __restrict__ R2 = A.R2;
+  double* __restrict__ S2 = A.S2;
   gemm_tile32(n, kImuDim, blockIdx.y * 32, blockIdx.x * 32,  // T2 columns < 15 are zero
               [&](int k, int a) { return TP[(size_t)a * ld + k]; },
               [&](int k, int b) { return T2[(size_t)b * ld + k]; },
@@ -100,9 +116,16 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_s(int n, int ld, const do
 
 // P <- P - W^T W (lower-triangular tile pairs; written in the filter precision, exactly symmetric by construction)
 template <class S>
-__global__ void __launch_bounds__(kGemmThreads) k_syrk(int n, int ld, const double* __restrict__ Wm, S* __restrict__ P, int ldp,
-                                            const int* __restrict__ m_in) {
-  if (*m_in == 0) return;
+__global__ void __launch_bounds__(kGemmThreads) k_syrk(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  const UpdArgs<S>& A = args[blockIdx.z];
+  const int n = A.n, ld = A.ld, ldp = A.ldp;
+  const int nt32 = (n + 31) / 32;
+  if ((int)blockIdx.x >= nt32 * (nt32 + 1) / 2 || A.n_tracks == 0) return;
+  const double* __restrict__ Wm = A.W;
+  S* __restrict__ P = A.P;
+  if (*A.m_out == 0) return;
   int pidx = blockIdx.x, ta = 0;
   while (pidx >= ta + 1) { pidx -= ta + 1; ++ta; }  // (ta >= tb)
   const int tb = pidx;
@@ -112,6 +135,7 @@ __global__ void __launch_bounds__(kGemmThreads) k_syrk(int n, int ld, const doub
               [&](int a, int b, double v) {
                 if (b <= a) {
                   const S r = (S)((double)P[(size_t)a * ldp + b] - v);
+                  if (!isfinite((double)r)) A.m_out[2] = 1;  // MSCKF_B200_ERR_NUMERIC (benign race: every writer stores 1)
                   P[(size_t)a * ldp + b] = r;
                   P[(size_t)b * ldp + a] = r;
                 }

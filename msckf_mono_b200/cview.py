@@ -50,6 +50,38 @@ def marginalize_batch(filters, threads=8):
     f0._chk(f0._f("marginalize_batch")(arr, C.c_int(len(filters)), C.c_int(int(threads))), "marginalize_batch")
 
 
+class FilterBatch:
+    """msckf_mono::MSCKFBatch<_S> through the C view: a persistent device batch over engine filters of one dtype."""
+
+    def __init__(self, filters, threads=1):
+        self.filters = list(filters)
+        f0 = self.filters[0]
+        self.lib = f0.lib
+        arr = (C.c_void_p * len(self.filters))(*[f.h for f in self.filters])
+        self.h = C.c_void_p()
+        f0._chk(self.lib.msckf_mono_batch_create(arr, C.c_int(len(self.filters)), C.c_int(int(threads)), C.byref(self.h)), "batch_create")
+
+    def marginalize(self):
+        self.filters[0]._chk(self.lib.msckf_mono_batch_marginalize(self.h), "batch_marginalize")
+
+    def handle(self):
+        fn = self.lib.msckf_mono_batch_handle
+        fn.restype = C.c_void_p
+        return fn(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.msckf_mono_batch_destroy.argtypes = [C.c_void_p]
+            self.lib.msckf_mono_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class CFilter:
     """MSCKF<_S> surface over a C view.  dtype: np.float32 or np.float64."""
 

@@ -15,6 +15,9 @@ struct msckf_b200_engine {
   int dtype = 0, M = 0, max_clones = 0;
   double imu[19] = {0};
   std::vector<int> last_len;  // observations per track of the pending batch
+  std::vector<int> buf_off, buf_idx;  // msckf_b200_input_buffer: host arrays the caller packs into
+  std::vector<double> buf_obs, buf_pfg;
+  long long imu_readings = 0;
   int pending = 0, mode = 0;
   long long updates = 0, launches = 0;
 };
@@ -39,15 +42,23 @@ int msckf_b200_initialize(msckf_b200_engine* e, const void*, const void*, const 
   e->M = 0;
   return 0;
 }
-int msckf_b200_propagate(msckf_b200_engine*, const void*) { return 0; }
+int msckf_b200_propagate(msckf_b200_engine* e, const void*) { e->imu_readings++; return 0; }
+int msckf_b200_propagate_n(msckf_b200_engine* e, const void*, int k) { e->imu_readings += k; return 0; }
+int msckf_b200_input_buffer(msckf_b200_engine* e, int n_tracks, int n_obs, msckf_b200_tracks* out) {
+  e->buf_off.assign(n_tracks + 1, 0); e->buf_idx.assign(n_obs + 1, 0); e->buf_obs.assign(2 * n_obs + 2, 0.0); e->buf_pfg.assign(3 * n_tracks + 3, 0.0);
+  out->n_tracks = n_tracks; out->obs_offset = e->buf_off.data(); out->clone_index = e->buf_idx.data();
+  out->obs = e->buf_obs.data(); out->p_f_G = e->buf_pfg.data();
+  return 0;
+}
 int msckf_b200_augment(msckf_b200_engine* e) {
-  if (e->M >= e->max_clones) return fail(MSCKF_B200_ERR_CAPACITY, "stub: too many clones");
+  if (e->M >= 192) return fail(MSCKF_B200_ERR_CAPACITY, "stub: window above the engine's hard limit");  // (capacities grow on demand)
   e->M++;
   return 0;
 }
 int msckf_b200_stage(msckf_b200_engine* e, int mode, const msckf_b200_tracks* tr) {
   if (e->pending) return fail(MSCKF_B200_ERR_STATE, "stub: previous update not fetched");
   e->last_len.clear();
+  if (tr->n_tracks > 0 && tr->obs_offset[0] != 0) return fail(MSCKF_B200_ERR_ARG, "stub: obs_offset[0] must be 0");
   for (int t = 0; t < tr->n_tracks; ++t) {
     const int L = tr->obs_offset[t + 1] - tr->obs_offset[t];
     if (L < 1 || L > 98) return fail(MSCKF_B200_ERR_ARG, "stub: bad track length");
@@ -91,6 +102,30 @@ int msckf_b200_update_batch(msckf_b200_engine** es, int n, int mode, const msckf
   for (int i = 0; i < n; ++i) { int rc = msckf_b200_update(es[i], mode, &tr[i], reps ? &reps[i] : nullptr); if (rc) return rc; }
   return 0;
 }
+struct msckf_b200_batch { std::vector<msckf_b200_engine*> es; long long launches = 0; };
+int msckf_b200_batch_create(msckf_b200_engine** es, int n, msckf_b200_batch** out) { auto* b = new msckf_b200_batch(); b->es.assign(es, es + n); *out = b; return 0; }
+int msckf_b200_batch_destroy(msckf_b200_batch* b) { delete b; return 0; }
+int msckf_b200_batch_stage(msckf_b200_batch* b, int mode, const msckf_b200_tracks* tr, int) {
+  for (size_t i = 0; i < b->es.size(); ++i) { int rc = msckf_b200_stage(b->es[i], mode, &tr[i]); if (rc) return rc; }
+  return 0;
+}
+int msckf_b200_batch_launch(msckf_b200_batch* b) { for (auto* e : b->es) msckf_b200_launch(e); b->launches++; return 0; }
+int msckf_b200_batch_launch_timed(msckf_b200_batch* b, float* ms) { if (ms) *ms = 0; return msckf_b200_batch_launch(b); }
+int msckf_b200_batch_update_async(msckf_b200_batch* b, int mode, const msckf_b200_tracks* tr, int t) {
+  int rc = msckf_b200_batch_stage(b, mode, tr, t);
+  return rc ? rc : msckf_b200_batch_launch(b);
+}
+int msckf_b200_batch_fetch(msckf_b200_batch* b, msckf_b200_report* reps) {
+  for (size_t i = 0; i < b->es.size(); ++i) { int rc = msckf_b200_fetch(b->es[i], reps ? &reps[i] : nullptr); if (rc) return rc; }
+  return 0;
+}
+int msckf_b200_batch_update(msckf_b200_batch* b, int mode, const msckf_b200_tracks* tr, msckf_b200_report* reps, int t) {
+  int rc = msckf_b200_batch_update_async(b, mode, tr, t);
+  return rc ? rc : msckf_b200_batch_fetch(b, reps);
+}
+int msckf_b200_batch_kernel_times(msckf_b200_batch*, float*, const char**, int) { return 0; }
+long long msckf_b200_batch_launch_count(const msckf_b200_batch* b) { return b->launches; }
+void* msckf_b200_batch_stream(msckf_b200_batch*) { return nullptr; }
 int msckf_b200_kernel_times(msckf_b200_engine*, float*, const char**, int) { return 0; }
 int msckf_b200_tail_profile(msckf_b200_engine*, unsigned long long*, int) { return 0; }
 int msckf_b200_prune(msckf_b200_engine* e, const int* keep, int n_keep) {

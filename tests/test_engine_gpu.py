@@ -285,6 +285,64 @@ def test_batched_entry_point_matches_individual_updates():
         assert a.counters() == b.counters()
 
 
+def test_persistent_batch_over_a_stream_is_bit_identical():
+    """msckf_mono::MSCKFBatch (persistent device batch; the filters share its stream): four filters streamed in lockstep with
+    propagate / augment / update / addFeatures per filter and ONE batched marginalize per frame -- including frames where some
+    members have nothing queued -- end bit-identical to the same filters run alone."""
+    from msckf_mono_b200.cview import FilterBatch
+    wls = [synth.make_stream_workload(n_frames=40, seq=50 + i, max_features=25 + 5 * i, max_track_length=8 + 2 * i, max_cam_states=8 + i) for i in range(4)]
+    solo, grp = [], []
+    for wl in wls:
+        a, b = make_engine(np.float32), make_engine(np.float32)
+        for f in (a, b):
+            f.initialize(wl["camera"], wl["noise"], wl["params"], wl["imu_state"])
+        solo.append(a); grp.append(b)
+    fb = FilterBatch(grp, threads=2)
+    for k in range(40):
+        for i, wl in enumerate(wls):
+            fr = wl["frames"][k]
+            for f in (solo[i], grp[i]):
+                for (w, acc, dT) in fr["imu"]:
+                    f.propagate(w, acc, dT)
+                f.augmentState(fr["state_id"], fr["time"])
+                f.update(*fr["update"])
+                f.addFeatures(*fr["add"])
+            solo[i].marginalize()
+        fb.marginalize()
+        for i in range(4):
+            ra, rb = solo[i].lastReport(), grp[i].lastReport()
+            assert np.array_equal(ra["accepted"], rb["accepted"]) and np.array_equal(ra["gamma"], rb["gamma"]), (k, i)
+            solo[i].pruneEmptyStates(); grp[i].pruneEmptyStates()
+    for a, b in zip(solo, grp):
+        assert a.counters()["n_updates"] > 10 and a.counters() == b.counters()
+        assert np.array_equal(a.getCovariance(), b.getCovariance())
+        assert np.array_equal(a.getImuState()["p_I_G"], b.getImuState()["p_I_G"])
+    fb.close()
+    # after the batch is gone the filters run on their own streams again
+    grp[0].marginalize()
+
+
+def test_window_growth_and_single_observation_tracks():
+    """Capacities are initial sizes (the reference's window and track lists are unbounded std::vectors): a filter created
+    for 6 clones / 8 tracks grows through 14 clones and 40 tracks and matches a filter that was created large.  A track
+    with one observation (min_track_length = 1) is reported as rejected instead of failing the batch."""
+    wl = synth.make_window_workload(n_features=40, n_clones=14, seq=4)
+    small = make_engine(np.float64, max_clones=6, max_tracks=8, max_obs=16)
+    big = make_engine(np.float64, max_clones=40, max_tracks=512, max_obs=512 * 30)
+    synth.drive(small, wl)
+    synth.drive(big, wl)
+    assert np.array_equal(small.getCovariance(), big.getCovariance())
+    assert np.array_equal(small.lastReport()["accepted"], big.lastReport()["accepted"])
+    from msckf_mono_b200 import capi
+    e = capi.Engine(np.float64, borrowed=big.engineHandle())
+    M = e.num_clones()
+    off = np.array([0, 1, 4], dtype=np.int32)          # track 0: one observation; track 1: three
+    idx = np.array([0, 0, 1, 2], dtype=np.int32)
+    obs = np.zeros(8)
+    rep = e.update(capi.MARGINALIZE, capi.TrackBatch(off, obs, idx, np.float64))
+    assert M >= 3 and rep["accepted"][0] == 0
+
+
 def test_c_abi_update_batch_matches_separate_updates():
     """`msckf_b200_update_batch` on the raw C-ABI: engines whose state was copied from driven filters, the queued batches
     replayed through the batched entry point -> same m, rank, accept flags and bit-identical covariance as one-by-one."""

@@ -150,6 +150,8 @@ int msckf_b200_num_clones(msckf_b200_engine* e);
 int msckf_b200_get_state(msckf_b200_engine* e, void* imu, void* clone_poses);
 /* full (15+6M)^2 covariance, row-major, dtype scalars */
 int msckf_b200_get_covariance(msckf_b200_engine* e, void* out);
+/* overwrite the covariance (same layout; checkpoint restore, Monte-Carlo initialisation) */
+int msckf_b200_set_covariance(msckf_b200_engine* e, const void* in);
 /* counters[0..7]: num_feature_tracks_residualized_, pfg_shifted, pfg_oob, n_updates, last m, last rank, 0, 0 */
 int msckf_b200_get_counters(msckf_b200_engine* e, long long* counters);
 /* last delta-x (fp64), returns its length */
@@ -159,7 +161,9 @@ int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap);
  *              2 = replay the update's kernel sequence as a CUDA graph when the batch signature repeats (default on);
  *              3 = fuse the forward substitution into the blocked Cholesky of the tail kernel where the window allows it
  *                  (15 + 6M <= 255; default on; 0 = always run it as a separate sweep -- same results up to rounding);
- *              4 = launch the update's kernels with programmatic dependent launch (default on) */
+ *              4 = launch the update's kernels with programmatic dependent launch (default on);
+ *              5 = Gram products of the compression on the FP64 tensor-core path (mma.sync m8n8k4 f64, SASS DMMA; default on;
+ *                  0 = SIMT DFMA tiles -- same results to fp64 rounding) */
 int msckf_b200_set_option(msckf_b200_engine* e, int key, double value);
 /* checkpoint / resume: copy the complete filter state of src into dst (same dtype and capacities) */
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src);

@@ -241,6 +241,16 @@ class Engine:
         check(lib().msckf_b200_get_covariance(self.h, out.ctypes.data_as(C.c_void_p)), "msckf_b200_get_covariance")
         return out
 
+    def set_covariance(self, P):
+        P = np.ascontiguousarray(P, dtype=self.dtype)
+        check(lib().msckf_b200_set_covariance(self.h, P.ctypes.data_as(C.c_void_p)), "msckf_b200_set_covariance")
+
+    def poison_covariance(self):
+        """test hook: a NaN in the IMU block (exercises MSCKF_B200_ERR_NUMERIC)"""
+        P = self.covariance()
+        P[0, 0] = np.nan
+        self.set_covariance(P)
+
     def delta_x(self):
         out = np.zeros(15 + 6 * 128)
         n = check(lib().msckf_b200_last_delta_x(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(len(out))), "last_delta_x")

@@ -115,6 +115,25 @@ template <class S> __device__ __forceinline__ S trsqrt(S x);
 template <> __device__ __forceinline__ float trsqrt<float>(float x) { return rsqrtf(x); }
 template <> __device__ __forceinline__ double trsqrt<double>(double x) { return rsqrt(x); }
 template <class S> __device__ __forceinline__ S tabs(S x) { return x < S(0) ? -x : x; }
+// 1 / sqrt(p) on a dependent chain: float seed + two Newton steps in fp64 (a dozen instructions instead of the library's ~35)
+__device__ __forceinline__ double fast_rsqrt(double p) {
+  if (p > 1e-30 && p < 1e30) {
+    double y = (double)rsqrtf((float)p);
+    const double hp = 0.5 * p;
+    y = y * (1.5 - hp * y * y);
+    y = y * (1.5 - hp * y * y);
+    return y;
+  }
+  return rsqrt(p);
+}
+__device__ __forceinline__ float fast_rsqrt(float p) { return rsqrtf(p); }
+// tl -> (ti >= tj) of the lower triangle of a tile grid
+__device__ __forceinline__ void tri_tile_index(int tl, int& ti, int& tj) {
+  ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
+  while (ti * (ti + 1) / 2 > tl) --ti;
+  while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+  tj = tl - ti * (ti + 1) / 2;
+}
 
 // Eigen QuaternionBase::toRotationMatrix restated; q = (x,y,z,w); R row-major 3x3.
 template <class S>

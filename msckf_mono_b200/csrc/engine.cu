@@ -7,7 +7,10 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -85,7 +88,7 @@ inline size_t tail_smem(int n, int kind) { return kind == 0 ? mb::tail_fused_sme
 
 // grid / shared-memory shape of one (batched) update: what a captured graph is valid for
 struct LaunchShape {
-  int nf, mode, tri_gx, jac_gx, bd_gx, gram_gx, gram_gy, asm_gx, rows_gx, gemm_g, syrk_gx, tail_mask, pdl, pad_;
+  int nf, mode, tri_gx, jac_gx, bd_gx, gram_gx, gram_gy, asm_gx, rows_gx, gemm_g, syrk_gx, tail_mask, pdl, gram_mma;
   unsigned tri_smem, jac_smem, rows_smem, inj_smem, tail_smem[3];
   const void* args;  // device address of the UpdArgs array (moves only when the input arena is re-allocated)
   bool operator==(const LaunchShape& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
@@ -115,6 +118,7 @@ struct EngineBase {
   virtual int prune(const int*, int) = 0;
   virtual int get_state(void*, void*) = 0;
   virtual int get_covariance(void*) = 0;
+  virtual int set_covariance(const void*) = 0;
   virtual int get_counters(long long*) = 0;
   virtual int last_dx(double*, int) = 0;
   virtual int copy_from(const EngineBase*) = 0;
@@ -127,6 +131,7 @@ struct EngineBase {
   bool profile = false;
   bool use_graph = true;
   bool use_pdl = true;
+  bool gram_mma = true;        // option 5: Gram products on the FP64 tensor-core path (DMMA) instead of SIMT DFMA tiles
   bool no_fused_tail = false;  // option 3 = 0: substitution as a separate sweep even where the fused form fits
   int dtype = 0, device = 0, Mmax = 0, Tmax = 0, Omax = 0;
   int M = 0;
@@ -174,6 +179,56 @@ struct Plan {
   }
 };
 
+// A few persistent host threads that share the validation / packing of a batch's track arrays (spawning std::threads per call
+// costs more than packing eight 100 KB batches).
+struct WorkerPool {
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  std::function<void(int)> fn;
+  int n_items = 0, next = 0, active = 0, gen = 0;
+  bool quit = false;
+  void start(int n) {
+    for (int i = (int)th.size(); i < n; ++i) th.emplace_back([this] { loop(); });
+  }
+  void loop() {
+    int seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_go.wait(lk, [&] { return quit || gen != seen; });
+      if (quit) return;
+      seen = gen;
+      while (next < n_items) {
+        const int i = next++;
+        lk.unlock();
+        fn(i);
+        lk.lock();
+      }
+      if (--active == 0) cv_done.notify_all();
+    }
+  }
+  // run f(0..n-1) on the pool's threads plus the caller
+  void run(int n, const std::function<void(int)>& f) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      fn = f; n_items = n; next = 0; active = (int)th.size(); gen++;
+    }
+    cv_go.notify_all();
+    for (;;) {
+      int i;
+      { std::lock_guard<std::mutex> lk(mu); if (next >= n_items) break; i = next++; }
+      f(i);
+    }
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return active == 0; });
+  }
+  ~WorkerPool() {
+    { std::lock_guard<std::mutex> lk(mu); quit = true; }
+    cv_go.notify_all();
+    for (auto& t : th) t.join();
+  }
+};
+
 // RAII guard: a failure between BeginCapture and EndCapture must not leave the stream in capture mode
 struct CaptureGuard {
   cudaStream_t s;
@@ -211,6 +266,7 @@ struct Ctx : CtxBase {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   int st_mode = -1;
   bool staged = false, timed_region = false;
+  WorkerPool pool;
   // graph cache
   struct Cached { LaunchShape shape; cudaGraphExec_t exec; int nodes; unsigned long long stamp; };
   std::vector<Cached> graphs;
@@ -382,6 +438,9 @@ struct Engine : EngineBase {
     CK(cudaMemsetAsync(d_prof, 0, sizeof(unsigned long long) * 80, stream));
     RC(alloc_window());
     RC(alloc_batchws());
+    // the private context's packed arenas, sized for a full batch (no pinned allocation inside the first update)
+    RC(solo.in.ensure(solo.args_bytes() + up256(Plan<S>::in_bytes(Tmax, Omax)), nullptr));
+    RC(solo.rep.ensure(up256(Plan<S>::rep_bytes(Tmax)), nullptr));
     CK(cudaMallocHost(&h_st, sizeof(mb::DevState<S>)));
     memset(h_st, 0, sizeof(mb::DevState<S>));
     RC(set_func_attrs());
@@ -512,7 +571,7 @@ struct Engine : EngineBase {
     if (kchunk < mb::GK) kchunk = mb::GK;
     nsplit = std::max(1, (a.K + kchunk - 1) / kchunk);
     a.nsplit = nsplit; a.kchunk = kchunk;
-    a.has_yf = (mb::jac_smem_bytes<S>(p.Lmax, M, true) <= kSmemBudget) ? 1 : 0;
+    a.has_yf = 0;  // (round 1's single-warp gate copy is gone: the gate Cholesky is blocked over the whole CTA)
     a.tail_kind = pick_tail(a.n, no_fused_tail);
     a.rank_thr = rank_thr;
     a.obs_off = p.d_off; a.obs = p.d_obs; a.clone_idx = p.d_idx; a.pfg_given = p.d_pfg_in;
@@ -593,6 +652,16 @@ struct Engine : EngineBase {
     CK(cudaMemcpy2DAsync(out, sizeof(S) * n, d_P, sizeof(S) * ldp, sizeof(S) * n, n, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     return n;
+  }
+
+  int set_covariance(const void* in) override {
+    if (!in) return fail(MSCKF_B200_ERR_ARG, "null argument");
+    if (busy) return fail(MSCKF_B200_ERR_STATE, "set_covariance with an un-fetched update pending");
+    CK(cudaSetDevice(device));
+    const int n = 15 + 6 * M;
+    CK(cudaMemcpy2DAsync(d_P, sizeof(S) * ldp, in, sizeof(S) * n, sizeof(S) * n, n, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));  // `in` is caller memory
+    return 0;
   }
 
   int get_counters(long long* c) override {
@@ -728,11 +797,8 @@ int Ctx<S>::stage(int mode, const msckf_b200_tracks* tracks, int threads) {
       for (int i = 0; i < nf; ++i) { const int r = fn(i); if (r != 0) return r; }
       return 0;
     }
-    std::vector<std::thread> pool;
-    auto work = [&](int w) { for (int i = w; i < nf; i += T) { rc[i] = fn(i); if (rc[i] != 0) err[i] = g_err; } };
-    for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
-    work(0);
-    for (auto& t : pool) t.join();
+    pool.start(T - 1);
+    pool.run(nf, [&](int i) { rc[i] = fn(i); if (rc[i] != 0) err[i] = g_err; });
     for (int i = 0; i < nf; ++i) if (rc[i] != 0) return fail(rc[i], err[i]);
     return 0;
   };
@@ -806,6 +872,9 @@ int Ctx<S>::launch() {
   sh.syrk_gx = sh.gemm_g * (sh.gemm_g + 1) / 2;
   sh.inj_smem = (unsigned)(sizeof(double) * nmax_);
   sh.pdl = (eng[0]->use_pdl && !profile()) ? 1 : 0;
+  // FP64 tensor-core Gram products where they win (measured, profiles/r02_dmma.md): batches and large track counts; one small
+  // filter is latency-bound either way and the 256-thread SIMT tile is a little quicker there
+  sh.gram_mma = (eng[0]->gram_mma && (nf > 1 || 3 * Nmax >= 1800)) ? 1 : 0;
   const bool want_graph = eng[0]->use_graph && !profile();
   if (want_graph) {
     for (auto& g : graphs)
@@ -902,7 +971,8 @@ int Ctx<S>::run_kernels(const LaunchShape& sh) {
     launches++;
     mark("k_blockdiag");
     if (fork) CK(cudaEventRecord(ev_join, stream2));
-    CK(launch_k(mb::k_gram<S>, dim3(sh.gram_gx, sh.gram_gy, nf), dim3(256), 0, stream, false, 1, A));
+    if (sh.gram_mma) CK(launch_k(mb::k_gram_mma<S>, dim3(sh.gram_gx, sh.gram_gy, nf), dim3(128), 0, stream, false, 1, A));  // FP64 tensor cores (DMMA)
+    else CK(launch_k(mb::k_gram<S>, dim3(sh.gram_gx, sh.gram_gy, nf), dim3(256), 0, stream, false, 1, A));
     launches++;
     mark("k_gram");
     if (fork) CK(cudaStreamWaitEvent(stream, ev_join, 0));
@@ -922,12 +992,9 @@ int Ctx<S>::run_kernels(const LaunchShape& sh) {
     if (sh.tail_mask & 2) { CK(launch_k(mb::k_tail<S, 32>, dim3(kTailCluster, 1, nf), dim3(mb::kTailThreads), sh.tail_smem[1], stream, pdl, kTailCluster, A)); launches++; }
     if (sh.tail_mask & 4) { CK(launch_k(mb::k_tail<S, 16>, dim3(kTailCluster, 1, nf), dim3(mb::kTailThreads), sh.tail_smem[2], stream, pdl, kTailCluster, A)); launches++; }
     mark("k_tail");
-    CK(launch_k(mb::k_syrk<S>, dim3(sh.syrk_gx, 1, nf), dim3(mb::kGemmThreads), 0, stream, pdl, 1, A));
+    CK(launch_k(mb::k_syrk<S>, dim3(sh.syrk_gx, 1, nf), dim3(mb::kGemmThreads), 0, stream, pdl, 1, A));  // + dx = W^T y + state injection
     launches++;
     mark("k_syrk");
-    CK(launch_k(mb::k_inject<S>, dim3(1, 1, nf), dim3(1024), sh.inj_smem, stream, pdl, 1, A));
-    launches++;
-    mark("k_inject");
   }
   return 0;
 }
@@ -1027,6 +1094,7 @@ int msckf_b200_create(const msckf_b200_config* cfg, msckf_b200_engine** out) {
   else return fail(MSCKF_B200_ERR_ARG, "bad dtype");
   if (getenv("MSCKF_B200_NO_GRAPH")) b->use_graph = false;  // e.g. under ncu: profile plain launches
   if (getenv("MSCKF_B200_NO_PDL")) b->use_pdl = false;
+  if (getenv("MSCKF_B200_NO_DMMA")) b->gram_mma = false;
   if (getenv("MSCKF_B200_NO_FUSED_TAIL")) b->no_fused_tail = true;
   b->dtype = cfg->dtype; b->device = cfg->device; b->Mmax = cfg->max_clones; b->Tmax = cfg->max_tracks; b->Omax = cfg->max_obs;
   int rc = (cfg->dtype == MSCKF_B200_F32) ? static_cast<Engine<float>*>(b)->alloc() : static_cast<Engine<double>*>(b)->alloc();
@@ -1141,6 +1209,7 @@ int msckf_b200_prune(msckf_b200_engine* e, const int* keep, int n_keep) { return
 int msckf_b200_num_clones(msckf_b200_engine* e) { return e->impl->M; }
 int msckf_b200_get_state(msckf_b200_engine* e, void* imu, void* clone_poses) { return e->impl->get_state(imu, clone_poses); }
 int msckf_b200_get_covariance(msckf_b200_engine* e, void* out) { return e->impl->get_covariance(out); }
+int msckf_b200_set_covariance(msckf_b200_engine* e, const void* in) { return e->impl->set_covariance(in); }
 int msckf_b200_get_counters(msckf_b200_engine* e, long long* counters) { return e->impl->get_counters(counters); }
 int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap) { return e->impl->last_dx(out, cap); }
 int msckf_b200_kernel_times(msckf_b200_engine* e, float* ms, const char** names, int cap) { return e->impl->solo_ctx()->kernel_times(ms, names, cap); }
@@ -1151,6 +1220,7 @@ int msckf_b200_set_option(msckf_b200_engine* e, int key, double value) {
   if (key == 2) { e->impl->use_graph = value != 0; e->impl->drop_graphs(); return 0; }
   if (key == 3) { e->impl->no_fused_tail = value == 0; return 0; }
   if (key == 4) { e->impl->use_pdl = value != 0; return 0; }
+  if (key == 5) { e->impl->gram_mma = value != 0; return 0; }
   return fail(MSCKF_B200_ERR_ARG, "unknown option");
 }
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src) { return dst->impl->copy_from(src->impl); }

@@ -280,14 +280,6 @@ __device__ __forceinline__ void block_sum3(double v[3], double* red /*[3 * JT/32
   }
 }
 
-// ---- single-warp Cholesky for the gate (up to 63 rows + the right-hand side as an extra row).
-// The matrix lives in shared memory as a padded row-major array Yf[64][kCholLd] holding the STRICTLY lower triangle
-// (upper triangle and diagonal slots are zero; the diagonal sits in dg[]), the right-hand side as row rho.  Lane l owns
-// rows l and l + 32.  Left-looking: per pivot one dot product per owned row over the finished columns, read 4 columns at
-// a time (the row stride keeps the 16-byte loads conflict-free) -- rolled loops on purpose: unrolling this by hand into
-// register-resident rows makes ~100 KB of straight-line code that runs once per CTA and is bound by instruction fetch.
-constexpr int kCholRows = 64, kCholLd = 68;
-
 __device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
   const float4 t = *reinterpret_cast<const float4*>(p);
   v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -297,59 +289,119 @@ __device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
   v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
 }
 
-// Left-looking with a one-pivot look-ahead (same scheme as tf_factor in tail_fused.cuh): the bracket of column k + 1,
-//   br(i) = a_{i,k+1} - sum_{j<k} L_ij L_{k+1,j},  is formed while pivot k's rsqrt is in flight; pivot k + 1 then only
-// needs   t_i = br(i) - L_ik L_{k+1,k}   (one shuffle + one FMA).  A row's slot of column k + 1 is zeroed once its original
-// value sits in the bracket, so every not-yet-final entry of a 16-column chunk reads as zero: no masking.
+// ---- gate Cholesky, blocked by panels of 8 columns, all JT threads of the CTA.
+// The matrix is the trailing block [3:, 3:] of the packed-lower 2L x 2L array Y (rho = 2L - 3 rows); the right-hand side
+// r[3:] rides along as row rho.  Only y = L^-1 r is wanted (gamma = |y|^2), so the factor itself is never written back.
+// Per panel:  (1) EVERY thread loads the 8 x 8 diagonal micro-block and factorises it redundantly in registers (static
+// indices, right-looking: the dependent chain of a pivot is rsqrt -> multiply -> one FMA) -- no shuffles, no barriers, no
+// pivot broadcast;  (2) every thread solves its own rows of the panel against that micro-block in registers (row rho = the
+// right-hand side: its 8 entries are final components of y);  (3) the solved panel goes to shared memory TRANSPOSED
+// ([8][Rp]: neighbouring threads touch neighbouring words), one barrier;  (4) trailing update in 4 x 4 register tiles over
+// the lower triangle, one barrier.  57 pivots cost 8 panels x 2 barriers instead of 57 dependent warp-wide steps
+// (round 1: one warp, shuffle + shared-memory round trip per pivot, ~350 ns each = 20 us of k_jac's 55).
+constexpr int kPW = 8;
 template <class S>
-__device__ __forceinline__ bool chol_warp(S* Yf, const S* dg, int rho, int lane) {
-  const S d0 = (lane < rho) ? dg[lane] : S(1), d1 = (lane + 32 < rho) ? dg[lane + 32] : S(1);
-  S* row0 = Yf + lane * kCholLd;
-  S* row1 = Yf + (lane + 32) * kCholLd;
-  S br0 = (lane == 0) ? d0 : row0[0], br1 = row1[0];  // brackets of column 0: the original entries
-  if (lane > 0) row0[0] = S(0);
-  row1[0] = S(0);
-  S lp0 = S(0), lp1 = S(0);  // the rows' entries of the previous column
-  __syncwarp();
-  for (int k = 0; k < rho; ++k) {
-    const S lk = __shfl_sync(0xffffffffu, (k >= 32) ? lp1 : lp0, k & 31);  // L_{k,k-1}
-    const S t0 = br0 - lp0 * lk, t1 = br1 - lp1 * lk;
-    const S piv = __shfl_sync(0xffffffffu, (k >= 32) ? t1 : t0, k & 31);
-    if (!(piv > S(0))) return false;
-    // next bracket: loads before this pivot's stores; 16 columns per round trip
-    const int k1 = k + 1;  // <= rho <= 63: a valid row (the right-hand side is row rho)
-    const S* prow = Yf + k1 * kCholLd;
-    const S an0 = (lane == k1) ? d0 : row0[k1], an1 = (lane + 32 == k1) ? d1 : row1[k1];
-    S a0[4] = {S(0), S(0), S(0), S(0)}, a1[4] = {S(0), S(0), S(0), S(0)};
-    for (int c0 = 0; c0 < k; c0 += 16) {
-      S p[4][4], x[4][4], y[4][4];
+__device__ __forceinline__ bool gate_chol_blocked(S* __restrict__ Y, S* __restrict__ r, int L2, S* __restrict__ PnT, int Rp) {
+  const int rho = L2 - 3, R = rho + 1, tid = threadIdx.x;
+  for (int e = tid; e < kPW * Rp; e += JT) PnT[e] = S(0);  // (rows R..Rp-1 of a partial tile must read as zero)
+  __syncthreads();
+  for (int p0 = 0; p0 < rho; p0 += kPW) {
+    const int w = min(kPW, rho - p0);
+    // (1) diagonal micro-block: lower triangle in registers, identity padding beyond w
+    S Lm[kPW][kPW], inv[kPW];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) { ld4(prow + c0 + 4 * v, p[v]); ld4(row0 + c0 + 4 * v, x[v]); ld4(row1 + c0 + 4 * v, y[v]); }
+    for (int a = 0; a < kPW; ++a)
 #pragma unroll
-      for (int v = 0; v < 4; ++v)
+      for (int b = 0; b <= a; ++b) Lm[a][b] = (a < w) ? Y[pk(3 + p0 + a, 3 + p0 + b)] : ((a == b) ? S(1) : S(0));
+    bool ok = true;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { a0[u] += x[v][u] * p[v][u]; a1[u] += y[v][u] * p[v][u]; }
+    for (int j = 0; j < kPW; ++j) {
+      const S d = Lm[j][j];
+      if (!(d > S(0))) ok = false;
+      const S iv = fast_rsqrt(d);
+      inv[j] = iv;
+#pragma unroll
+      for (int a = j + 1; a < kPW; ++a) Lm[a][j] *= iv;
+#pragma unroll
+      for (int b = j + 1; b < kPW; ++b)
+#pragma unroll
+        for (int a = b; a < kPW; ++a) Lm[a][b] -= Lm[a][j] * Lm[b][j];
     }
-    const S inv = trsqrt<S>(piv);
-    const S l0 = (lane > k) ? t0 * inv : S(0), l1 = (lane + 32 > k) ? t1 * inv : S(0);
-    br0 = an0 - ((a0[0] + a0[1]) + (a0[2] + a0[3]));
-    br1 = an1 - ((a1[0] + a1[1]) + (a1[2] + a1[3]));
-    if (lane > k && lane <= rho) row0[k] = l0;
-    if (lane + 32 > k && lane + 32 <= rho) row1[k] = l1;
-    if (lane > k1) row0[k1] = S(0);      // the original values live in the brackets now
-    if (lane + 32 > k1) row1[k1] = S(0);
-    lp0 = l0; lp1 = l1;
-    __syncwarp();
+    if (!ok) return false;  // (every thread computed the same micro-block: uniform)
+    // (2) rows below the micro-block, and the right-hand side
+    const int q0 = p0 + w;
+    for (int i = q0 + tid; i < R; i += JT) {
+      S x[kPW];
+      if (i < rho) {
+        const S* row = Y + pk(3 + i, 3 + p0);
+#pragma unroll
+        for (int j = 0; j < kPW; ++j) x[j] = (j < w) ? row[j] : S(0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kPW; ++j) x[j] = (j < w) ? r[3 + p0 + j] : S(0);
+      }
+#pragma unroll
+      for (int j = 0; j < kPW; ++j) {
+        x[j] *= inv[j];
+#pragma unroll
+        for (int jj = j + 1; jj < kPW; ++jj) x[jj] -= x[j] * Lm[jj][j];
+      }
+#pragma unroll
+      for (int j = 0; j < kPW; ++j) PnT[j * Rp + i] = x[j];
+      if (i == rho) {
+#pragma unroll
+        for (int j = 0; j < kPW; ++j) if (j < w) r[3 + p0 + j] = x[j];  // final components of y
+      }
+    }
+    __syncthreads();
+    // (4) trailing update: rows q0..R-1, columns q0..rho-1, lower triangle, 4 x 4 tiles (q0 is a multiple of 8 here)
+    const int nrows = R - q0;
+    if (nrows > 1) {
+      const int nt = (nrows + 3) >> 2, ntile = nt * (nt + 1) / 2;
+      for (int q = tid; q < ntile; q += JT) {
+        int ti, tj;
+        tri_tile_index(q, ti, tj);
+        const int r0 = q0 + 4 * ti, c0 = q0 + 4 * tj;
+        S acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = S(0);
+#pragma unroll
+        for (int j = 0; j < kPW; ++j) {
+          S pr[4], pc[4];
+          ld4(PnT + j * Rp + r0, pr);
+          ld4(PnT + j * Rp + c0, pc);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] += pr[a] * pc[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int row = r0 + a;
+          if (row >= R) continue;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int col = c0 + b;
+            if (col < rho && col <= row) {
+              if (row < rho) Y[pk(3 + row, 3 + col)] -= acc[a][b]; else r[3 + col] -= acc[a][b];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
   }
   return true;
 }
 
 template <class S>
-__host__ __device__ inline size_t jac_smem_bytes(int L, int M, bool with_yf = true) {
+__host__ __device__ inline size_t jac_smem_bytes(int L, int M, bool /*unused: kept for the call sites*/ = true) {
   // bar 16 | poses M*8 S | U64 6L doubles | X 12L | r 2L | V 6L | W 6L | F 6L | Ypacked L(2L+1)  (S) | pad |
-  // Yf 64 x 68 + dg 64 (S): the single-warp gate Cholesky's row-major copy
+  // PnT 8 x Rp (S): the gate Cholesky's transposed panel, Rp = (2L - 2 + 3) & ~3
   return 16 + sizeof(S) * kPoseStride * (size_t)M + 16 + sizeof(double) * 6 * (size_t)L +
-         sizeof(S) * ((size_t)32 * L + (size_t)L * (2 * L + 1)) + 32 + (with_yf ? sizeof(S) * ((size_t)kCholRows * kCholLd + kCholRows) : 0);
+         sizeof(S) * ((size_t)32 * L + (size_t)L * (2 * L + 1)) + 32 + sizeof(S) * (size_t)kPW * (size_t)((2 * L + 1) & ~3) + 16;
 }
 
 // Ordered stacking (msckf.h:433-445): the exclusive prefix sum of the accepted blocks' row counts, computed by whichever
@@ -491,9 +543,8 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
   S* wv = V + 3 * L2;   // [2L][3]  W = Y V
   S* Fv = wv + 3 * L2;  // [2L][3]  F of the two-sided transform
   S* Y = Fv + 3 * L2;
-  S* Yf = reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(Y + (size_t)L * (L2 + 1)) + 15) & ~uintptr_t(15));  // [64][68]
-  S* dgv = Yf + kCholRows * kCholLd;  // [64]
-  const bool warp_chol = a.has_yf && (L2 - 3 + 1 <= kCholRows);  // the gate matrix and its right-hand side fit the single-warp form
+  S* PnT = reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(Y + (size_t)L * (L2 + 1)) + 15) & ~uintptr_t(15));  // [8][Rp]
+  const int Rp = (L2 + 1) & ~3;  // >= rho + 1 = 2L - 2, multiple of 4
   const int* idx = a.clone_idx + o0;
   const S* z = a.obs + 2 * (size_t)o0;
   const DevState<S>* st = a.st;
@@ -778,82 +829,24 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
     }
   }
   __syncthreads();
-  // only the trailing block [3:, 3:] is used below.  Single-warp gate: the transformed block goes straight into the padded
-  // row-major copy (strictly lower part; diagonal + u_var into dgv; right-hand side as row rho).
+  // only the trailing block [3:, 3:] is used below: S = (Q^T Y Q)[3:,3:] + u_var I, in place in the packed array
   const S uvar = st->u_var;
   const int rho = L2 - 3;
-  if (warp_chol) {
-    for (int e = tid; e < kCholRows * kCholLd; e += JT) {
-      const int q = e / kCholLd, cc = e % kCholLd;
-      Yf[e] = (q == rho && cc < rho) ? r[3 + cc] : S(0);
-    }
-    __syncthreads();
-  }
   for (int ar = 3 + warp; ar < L2; ar += JT / 32) {  // one row per warp, lanes along the row
     const S va0 = V[3 * ar], va1 = V[3 * ar + 1], va2 = V[3 * ar + 2];
     const S fa0 = Fv[3 * ar], fa1 = Fv[3 * ar + 1], fa2 = Fv[3 * ar + 2];
     for (int b = 3 + lane; b <= ar; b += 32) {
       const S val = Y[pk(ar, b)] - ((va0 * Fv[3 * b] + va1 * Fv[3 * b + 1] + va2 * Fv[3 * b + 2]) + (fa0 * V[3 * b] + fa1 * V[3 * b + 1] + fa2 * V[3 * b + 2]));
-      if (!warp_chol) Y[pk(ar, b)] = val;
-      else if (b < ar) Yf[(ar - 3) * kCholLd + (b - 3)] = val;
-      else dgv[ar - 3] = val + uvar;
+      Y[pk(ar, b)] = (b == ar) ? val + uvar : val;
     }
   }
   __syncthreads();
   stamp();  // two-sided transform
-  // S = Y[3:,3:] + u_var I ; Cholesky with the right-hand side r~[3:] riding along as an extra row
-  bool chol_ok = true;
+  // Cholesky with the right-hand side r~[3:] riding along as an extra row: y = L^-1 r~, gamma = |y|^2
+  const bool chol_ok = gate_chol_blocked<S>(Y, r, L2, PnT, Rp);
   S gacc = 0;
-  if (warp_chol) {
-    __shared__ int s_ok;
-    if (warp == 0) {
-      const bool ok = chol_warp<S>(Yf, dgv, rho, lane);
-      if (lane == 0) s_ok = ok ? 1 : 0;
-    }
-    __syncthreads();
-    chol_ok = s_ok != 0;
-    for (int j = tid; j < rho; j += JT) { const S v = Yf[rho * kCholLd + j]; gacc += v * v; }
-  } else {
-    // left-looking, one matrix row per thread (threads >= rows idle).  Per column: one dot product over the finished
-    // columns (contiguous in the packed row), the pivot broadcast through shared memory, two barriers.
-    for (int j = 3 + tid; j < L2; j += JT) Y[pk(j, j)] += uvar;
-    __shared__ S s_piv;
-    for (int j = 3; j < L2; ++j) {
-      __syncthreads();
-      // rows i = j .. L2-1 and the extra row (index L2): strided over the CTA's threads
-      S sv[2] = {S(0), S(0)};
-      int cnt = 0;
-      for (int i = j + tid; i <= L2; i += JT, ++cnt) {
-        const S* rowi = (i < L2) ? (Y + pk(i, 0)) : nullptr;
-        const S* rowj = Y + pk(j, 0);
-        S sacc = (i < L2) ? rowi[j] : r[j];
-        {
-          const S* src = (i < L2) ? rowi : r;  // the extra row is the right-hand side
-          S p4[4] = {S(0), S(0), S(0), S(0)};  // 4 partial sums: short FMA chains, loads issued back to back
-          int cc = 3;
-          for (; cc + 4 <= j; cc += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) p4[u] += src[cc + u] * rowj[cc + u];
-          }
-          for (; cc < j; ++cc) p4[0] += src[cc] * rowj[cc];
-          sacc -= (p4[0] + p4[1]) + (p4[2] + p4[3]);
-        }
-        if (cnt < 2) sv[cnt] = sacc;
-        if (i == j) s_piv = sacc;
-      }
-      __syncthreads();
-      const S dj = s_piv;
-      if (!(dj > S(0))) { chol_ok = false; break; }
-      const S inv = S(1) / tsqrt<S>(dj);
-      cnt = 0;
-      for (int i = j + tid; i <= L2; i += JT, ++cnt) {
-        const S v = sv[cnt < 2 ? cnt : 1] * inv;
-        if (i < L2) Y[pk(i, j)] = v; else r[j] = v;
-      }
-    }
-    __syncthreads();
-    for (int j = 3 + tid; j < L2; j += JT) gacc += r[j] * r[j];
-  }
+  for (int j = 3 + tid; j < L2; j += JT) gacc += r[j] * r[j];
+  (void)rho;
   S gam = block_sum(gacc, reds);
   const int acc = chol_ok && (gam < st->chi2[L]);  // table[dof+1], dof = L-1 (msckf.h:433,:1117)
   if (!chol_ok) gam = S(1e30);

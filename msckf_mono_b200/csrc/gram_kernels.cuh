@@ -78,6 +78,84 @@ __global__ void __launch_bounds__(256) k_gram(const UpdArgs<S>* __restrict__ arg
     }
 }
 
+// The same partial Gram products on the FP64 tensor-core path: mma.sync.aligned.m8n8k4.row.col.f64 (SASS: DMMA), 4 warps per
+// CTA, one 32 x 32 output tile per CTA, each warp a 16 x 16 quadrant = 2 x 2 MMA tiles for G1 and for G2 (12 DMMA per 4-deep
+// k-step against 8 fragment loads; the SIMT form above needs 32 LDS + 48 DFMA warp instructions for the same k-step).
+// Fragments (PTX ISA, m8n8k4 .f64): A (8x4, row): lane l holds A[l/4][l%4]; B (4x8, col): lane l holds B[l%4][l/4];
+// C/D (8x8): lane l holds C[l/4][2(l%4)] and C[l/4][2(l%4)+1].  Here A = Z^T (or Yq^T) and B = Z (or Yq) of a k-slab
+// staged in shared memory k-major with a row stride of 36 doubles (== 4 mod 16: the 16 lanes of a half warp hit 16 banks pairs).
+// Accumulation order differs from k_gram (fixed, deterministic): results agree to fp64 rounding.
+constexpr int GL = GT + 4;
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+template <class S>
+__global__ void __launch_bounds__(128) k_gram_mma(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  const UpdArgs<S>& A = args[blockIdx.z];
+  const int K = A.K, c = A.n - kImuDim, kchunk = A.kchunk;
+  const double* __restrict__ Z = A.Z;
+  const double* __restrict__ Yq = A.Yq;
+  __shared__ double sZa[GK][GL], sZb[GK][GL], sYa[GK][GL], sYb[GK][GL];
+  const int ntile = (c + GT - 1) / GT;
+  if ((int)blockIdx.x >= ntile * (ntile + 1) / 2 || (int)blockIdx.y >= A.nsplit || A.n_tracks == 0) return;
+  int pidx = blockIdx.x, ta = 0;
+  while (pidx >= ntile - ta) { pidx -= ntile - ta; ++ta; }
+  const int tb = ta + pidx;
+  const int split = blockIdx.y;
+  const int k0 = split * kchunk, k1 = min(K, k0 + kchunk);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;  // this warp's quadrant
+  const int fr = lane >> 2, fk = lane & 3;
+  double c1[2][2][2], c2[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { c1[i][j][0] = c1[i][j][1] = 0.0; c2[i][j][0] = c2[i][j][1] = 0.0; }
+  for (int kb = k0; kb < k1; kb += GK) {
+    for (int e = tid; e < GK * GT; e += 128) {
+      const int kk = e / GT, cc = e % GT;
+      const int k = kb + kk;
+      const int ca = ta * GT + cc, cb = tb * GT + cc;
+      const bool kin = k < k1;
+      sZa[kk][cc] = (kin && ca < c) ? Z[(size_t)k * c + ca] : 0.0;
+      sYa[kk][cc] = (kin && ca < c) ? Yq[(size_t)k * c + ca] : 0.0;
+      sZb[kk][cc] = (kin && cb < c) ? Z[(size_t)k * c + cb] : 0.0;
+      sYb[kk][cc] = (kin && cb < c) ? Yq[(size_t)k * c + cb] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < GK; ks += 4) {
+      double az[2], ay[2], bz[2], by[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { az[i] = sZa[ks + fk][wm + 8 * i + fr]; ay[i] = sYa[ks + fk][wm + 8 * i + fr]; }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { bz[j] = sZb[ks + fk][wn + 8 * j + fr]; by[j] = sYb[ks + fk][wn + 8 * j + fr]; }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          dmma(c1[i][j], az[i], bz[j]);
+          dmma(c2[i][j], az[i], by[j]);
+          dmma(c2[i][j], ay[i], bz[j]);
+        }
+    }
+    __syncthreads();
+  }
+  double* o1 = A.G1p + (size_t)split * c * c;
+  double* o2 = A.G2p + (size_t)split * c * c;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int ra = ta * GT + wm + 8 * i + fr, cb = tb * GT + wn + 8 * j + 2 * fk + q;
+        if (ra < c && cb < c) { o1[(size_t)ra * c + cb] = c1[i][j][q]; o2[(size_t)ra * c + cb] = c2[i][j][q]; }
+      }
+}
+
 // Block-diagonal terms, one CTA per clone: D1 = sum X^T X, D2 = sum X^T D X (6x6), b = sum X^T r (6),
 // over the accepted tracks' observations of that clone.  Deterministic (fixed feature->thread map, tree reduce).
 template <class S>

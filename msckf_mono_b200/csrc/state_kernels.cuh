@@ -85,9 +85,32 @@ struct PropBatch {
 
 template <class S>
 __global__ void __launch_bounds__(256) k_propagate(const PropBatch<S> pb) {
-  DevState<S>* st = pb.st;
+  // The IMU state, the 15 x 15 IMU block of P and (for windows up to 85 clones) the thread's columns of P_IC stay on chip
+  // across the readings of the batch: one global round trip per launch instead of one per reading and serial section.
+  DevState<S>* gst = pb.st;
+  __shared__ DevState<S> s_state;
+  DevState<S>* st = &s_state;
   S* __restrict__ P = pb.P;
   const int ldp = pb.ldp, M = pb.M;
+  {
+    static_assert(sizeof(DevState<S>) % 4 == 0, "DevState is copied word-wise");
+    const unsigned* src = reinterpret_cast<const unsigned*>(gst);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s_state);
+    for (int e = threadIdx.x; e < (int)(sizeof(DevState<S>) / 4); e += 256) dst[e] = src[e];
+  }
+  __shared__ S PII[225];
+  if (threadIdx.x < 225) PII[threadIdx.x] = P[(size_t)(threadIdx.x / 15) * ldp + threadIdx.x % 15];
+  const int c_all = 6 * M;
+  const bool cols_in_regs = c_all <= 512;
+  S vcol[2][15];
+  if (cols_in_regs) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int col = threadIdx.x + 256 * u;
+#pragma unroll
+      for (int k = 0; k < 15; ++k) vcol[u][k] = (col < c_all) ? P[(size_t)k * ldp + 15 + col] : S(0);
+    }
+  }
   __shared__ S F[225], Phi[225], A2[225], A4[225], A6[225], A8[225], Um[225], Vm[225], Tm[225], Id[225];
   __shared__ S G[15 * 12], GQ[15 * 12];
   __shared__ S CT[9];            // C_IG^T
@@ -250,45 +273,39 @@ __global__ void __launch_bounds__(256) k_propagate(const PropBatch<S> pb) {
   // (V - U) Phi = (V + U): partial-pivot LU on the 15x30 augmented system [den | num]
   if (t < 225) { Tm[t] = Vm[t] - Um[t]; Phi[t] = Vm[t] + Um[t]; }
   __syncthreads();
-  __shared__ int s_piv;
-  __shared__ S lcol[15];
-  for (int k = 0; k < 15; ++k) {
-    if (t == 0) {
+  // partial-pivot LU of the 15 x 30 system [den | num] and the back substitution on ONE warp (lane = column: 0..14 of den,
+  // 15..29 of num), __syncwarp only -- the CTA-wide form cost five block barriers per pivot.  Same operations in the same
+  // order as before (first largest |pivot|, multiplier by division, multiply-subtract).
+  if (t < 32) {
+    S* Mx = (t < 15) ? Tm : Phi;
+    const int j = (t < 15) ? t : t - 15;
+    for (int k = 0; k < 15; ++k) {
       int p = k;
-      S big = tabs(Tm[15 * k + k]);
-      for (int i = k + 1; i < 15; ++i)
-        if (tabs(Tm[15 * i + k]) > big) { big = tabs(Tm[15 * i + k]); p = i; }
-      s_piv = p;
-    }
-    __syncthreads();
-    const int p = s_piv;
-    if (p != k && t < 30) {
-      S* Mx = (t < 15) ? Tm : Phi;
-      const int j = t % 15;
-      const S tmp = Mx[15 * k + j]; Mx[15 * k + j] = Mx[15 * p + j]; Mx[15 * p + j] = tmp;
-    }
-    __syncthreads();
-    // eliminate below row k over the 30 columns of [den | num]
-    if (t < 15) lcol[t] = (t > k) ? Tm[15 * t + k] / Tm[15 * k + k] : S(0);
-    __syncthreads();
-    for (int e = t; e < 14 * 30; e += 256) {
-      const int i = e / 30 + 1, j = e % 30;  // rows 1..14 (only i > k active)
-      if (i > k) {
-        const S l = lcol[i];
-        if (j < 15) { if (j > k) Tm[15 * i + j] -= l * Tm[15 * k + j]; }
-        else Phi[15 * i + (j - 15)] -= l * Phi[15 * k + (j - 15)];
+      if (t == k) {
+        S big = tabs(Tm[15 * k + k]);
+        for (int i = k + 1; i < 15; ++i)
+          if (tabs(Tm[15 * i + k]) > big) { big = tabs(Tm[15 * i + k]); p = i; }
       }
+      p = __shfl_sync(0xffffffffu, p, k);
+      if (p != k && t < 30) { const S tmp = Mx[15 * k + j]; Mx[15 * k + j] = Mx[15 * p + j]; Mx[15 * p + j] = tmp; }
+      __syncwarp();
+      const S lmine = (t < 15 && t > k) ? Tm[15 * t + k] / Tm[15 * k + k] : S(0);  // lane i: multiplier of row i
+      __syncwarp();
+      for (int i = k + 1; i < 15; ++i) {
+        const S l = __shfl_sync(0xffffffffu, lmine, i);
+        if (t < 30 && (t >= 15 || j > k)) Mx[15 * i + j] -= l * Mx[15 * k + j];
+      }
+      if (t == k)
+        for (int i = k + 1; i < 15; ++i) Tm[15 * i + k] = S(0);
+      __syncwarp();
     }
-    __syncthreads();
-    if (t < 15 && t > k) Tm[15 * t + k] = S(0);
-    __syncthreads();
-  }
-  // back substitution: column j of Phi per thread
-  if (t < 15) {
-    for (int i = 14; i >= 0; --i) {
-      S s = Phi[15 * i + t];
-      for (int k = i + 1; k < 15; ++k) s -= Tm[15 * i + k] * Phi[15 * k + t];
-      Phi[15 * i + t] = s / Tm[15 * i + i];
+    // back substitution: column t of Phi per lane
+    if (t < 15) {
+      for (int i = 14; i >= 0; --i) {
+        S sacc = Phi[15 * i + t];
+        for (int k = i + 1; k < 15; ++k) sacc -= Tm[15 * i + k] * Phi[15 * k + t];
+        Phi[15 * i + t] = sacc / Tm[15 * i + i];
+      }
     }
   }
   __syncthreads();
@@ -336,27 +353,44 @@ __global__ void __launch_bounds__(256) k_propagate(const PropBatch<S> pb) {
     const int i = t / 15, j = t % 15;
     S s = 0;
     for (int k = 0; k < 12; ++k) s += GQ[12 * i + k] * G[12 * j + k];
-    A2[t] = P[(size_t)i * ldp + j] + s * dT;
+    A2[t] = PII[t] + s * dT;
   }
   __syncthreads();
   mm15(A4, Phi, A2);
   mm15_nt(A6, A4, Phi);
   if (t < 225) {
     const int i = t / 15, j = t % 15;
-    P[(size_t)i * ldp + j] = (A6[15 * i + j] + A6[15 * j + i]) / S(2.0);
+    PII[t] = (A6[15 * i + j] + A6[15 * j + i]) / S(2.0);
   }
-  const int c = 6 * M;
-  for (int col = t; col < c; col += 256) {
-    S v[15];
+  if (cols_in_regs) {
 #pragma unroll
-    for (int k = 0; k < 15; ++k) v[k] = P[(size_t)k * ldp + 15 + col];
+    for (int u = 0; u < 2; ++u) {
+      if (t + 256 * u < c_all) {
+        S nv[15];
 #pragma unroll
-    for (int i = 0; i < 15; ++i) {
-      S s = 0;
+        for (int i = 0; i < 15; ++i) {
+          S sacc = 0;
 #pragma unroll
-      for (int k = 0; k < 15; ++k) s += Phi[15 * i + k] * v[k];
-      P[(size_t)i * ldp + 15 + col] = s;
-      P[(size_t)(15 + col) * ldp + i] = s;
+          for (int k = 0; k < 15; ++k) sacc += Phi[15 * i + k] * vcol[u][k];
+          nv[i] = sacc;
+        }
+#pragma unroll
+        for (int i = 0; i < 15; ++i) vcol[u][i] = nv[i];
+      }
+    }
+  } else {
+    for (int col = t; col < c_all; col += 256) {
+      S v[15];
+#pragma unroll
+      for (int k = 0; k < 15; ++k) v[k] = P[(size_t)k * ldp + 15 + col];
+#pragma unroll
+      for (int i = 0; i < 15; ++i) {
+        S sacc = 0;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) sacc += Phi[15 * i + k] * v[k];
+        P[(size_t)i * ldp + 15 + col] = sacc;
+        P[(size_t)(15 + col) * ldp + i] = sacc;
+      }
     }
   }
   __syncthreads();
@@ -368,6 +402,28 @@ __global__ void __launch_bounds__(256) k_propagate(const PropBatch<S> pb) {
     }
   }
   __syncthreads();  // the next reading starts from the state and covariance written above
+  }
+  // ---- write back: IMU state, P_II, P_IC (and its transpose)
+  if (t == 0) {
+    for (int i = 0; i < 4; ++i) { gst->q_IG[i] = st->q_IG[i]; gst->q_IG_null[i] = st->q_IG_null[i]; }
+    for (int i = 0; i < 3; ++i) {
+      gst->v_I_G[i] = st->v_I_G[i]; gst->v_I_G_null[i] = st->v_I_G_null[i];
+      gst->p_I_G[i] = st->p_I_G[i]; gst->p_I_G_null[i] = st->p_I_G_null[i];
+    }
+  }
+  if (t < 225) P[(size_t)(t / 15) * ldp + t % 15] = PII[t];
+  if (cols_in_regs) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int col = t + 256 * u;
+      if (col < c_all) {
+#pragma unroll
+        for (int i = 0; i < 15; ++i) {
+          P[(size_t)i * ldp + 15 + col] = vcol[u][i];
+          P[(size_t)(15 + col) * ldp + i] = vcol[u][i];
+        }
+      }
+    }
   }
 }
 

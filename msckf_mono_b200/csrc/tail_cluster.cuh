@@ -387,77 +387,4 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(const UpdArgs<S>* __restr
 }
 
 
-// dx = W^T y, then the state correction of msckf.h:1373-1391.  Single CTA.
-template <class S>
-__global__ void __launch_bounds__(1024) k_inject(const UpdArgs<S>* __restrict__ args) {
-  pdl_wait();
-  const UpdArgs<S>& ua = args[blockIdx.z];
-  if (ua.n_tracks == 0) return;
-  const int n = ua.n, ld = ua.ld, M = ua.M;
-  const double* __restrict__ Wm = ua.W;
-  const double* __restrict__ yv = ua.y;
-  DevState<S>* st = ua.st;
-  S* __restrict__ poses = ua.poses;
-  double* __restrict__ dx_out = ua.dx;
-  const int* __restrict__ m_in = ua.m_out;
-  const int* __restrict__ rank_in = ua.rank_out;
-  extern __shared__ double sdx[];
-  const int tid = threadIdx.x;
-  if (*m_in == 0) {  // nothing accepted: the reference returns before touching the state (msckf.h:401-403,:1328)
-    for (int a = tid; a < n; a += 1024) dx_out[a] = 0.0;
-    return;
-  }
-  {
-    __shared__ double part[32][33];
-    const int al = tid & 31, kg = tid >> 5;
-    for (int a0 = 0; a0 < n; a0 += 32) {
-      const int a = a0 + al;
-      double s = 0.0;
-      if (a < n)
-        for (int k = kg; k < n; k += 32) s += Wm[(size_t)k * ld + a] * yv[k];
-      part[kg][al] = s;
-      __syncthreads();
-      if (kg == 0 && a < n) {
-        double t = 0.0;
-#pragma unroll
-        for (int g = 0; g < 32; ++g) t += part[g][al];
-        sdx[a] = t;
-        dx_out[a] = t;
-      }
-      __syncthreads();
-    }
-  }
-  if (tid == 0) {
-    const S dth[3] = {(S)sdx[0], (S)sdx[1], (S)sdx[2]};
-    S uq[4], qn[4];
-    build_update_quat(dth, uq);
-    quat_mul(uq, st->q_IG, qn);  // not renormalised (msckf.h:1376-1378)
-    for (int i = 0; i < 4; ++i) st->q_IG[i] = qn[i];
-    for (int i = 0; i < 3; ++i) {
-      st->b_g[i] += (S)sdx[3 + i];
-      st->v_I_G[i] += (S)sdx[6 + i];
-      st->b_a[i] += (S)sdx[9 + i];
-      st->p_I_G[i] += (S)sdx[12 + i];
-    }
-    st->n_updates += 1;
-    st->last_m = *m_in;
-    st->last_rank = *rank_in;
-    double nn = 0.0;
-    for (int a = 0; a < n; ++a) nn += sdx[a] * sdx[a];
-    st->last_dx_norm = sqrt(nn);
-    if (!isfinite(nn)) ua.m_out[2] = 1;  // non-finite delta-x (k_syrk flags a non-finite covariance entry the same way)
-    st->last_status = ua.m_out[2];
-  }
-  for (int ci = tid; ci < M; ci += 1024) {
-    S* ps = poses + kPoseStride * ci;
-    const S dth[3] = {(S)sdx[15 + 6 * ci], (S)sdx[16 + 6 * ci], (S)sdx[17 + 6 * ci]};
-    S uq[4], qn[4];
-    build_update_quat(dth, uq);
-    quat_mul(uq, ps, qn);
-    quat_normalize(qn);
-    ps[0] = qn[0]; ps[1] = qn[1]; ps[2] = qn[2]; ps[3] = qn[3];
-    ps[4] += (S)sdx[18 + 6 * ci]; ps[5] += (S)sdx[19 + 6 * ci]; ps[6] += (S)sdx[20 + 6 * ci];
-  }
-}
-
 }  // namespace mb

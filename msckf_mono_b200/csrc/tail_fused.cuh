@@ -27,16 +27,15 @@
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "tail_cluster.cuh"
+#include "tail_diag.cuh"
 
 namespace mb {
 
-constexpr int kFB = 32;        // block size of the fused form
-constexpr int kFLD = kFB + 2;  // row stride of the 32 x 32 shared blocks: even (16-byte loads), conflict-free per quarter warp
 
 __host__ __device__ inline size_t tail_fused_smem_bytes(int n) {
   const size_t ldt = (size_t)((n + 3) & ~3);
-  // DG, DA, LIG, LIA, WB [32][34] | PT_A, PT_G, Ws [32][ldt] | XT [32][32] | d0 [n] | idg, ida [32]
-  return sizeof(double) * (5 * (size_t)kFB * kFLD + 3 * (size_t)kFB * ldt + (size_t)kFB * kFB + ((n + 1) & ~1) + 2 * kFB) + 64;
+  // DG, DA, LIG, LIA, WB, DT [32][34] | PT_A, PT_G, Ws [32][ldt] | XT [32][32] | d0 [n] | idg, ida [32]
+  return sizeof(double) * (6 * (size_t)kFB * kFLD + 3 * (size_t)kFB * ldt + (size_t)kFB * kFB + ((n + 1) & ~1) + 2 * kFB) + 64;
 }
 
 __device__ __forceinline__ void tf_ld8(const double* p, double (&v)[8]) {
@@ -51,135 +50,13 @@ __device__ __forceinline__ void tf_ld4(const double* p, double (&v)[4]) {
   v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
 }
 
-// 1 / sqrt(p): float seed + two Newton steps (a dozen instructions instead of the library's ~35)
-__device__ __forceinline__ double tf_rsqrt(double p) {
-  if (p > 1e-30 && p < 1e30) {
-    double y = (double)rsqrtf((float)p);
-    const double hp = 0.5 * p;
-    y = y * (1.5 - hp * y * y);
-    y = y * (1.5 - hp * y * y);
-    return y;
-  }
-  return rsqrt(p);
-}
-
-// diagonal block -> shared [32][34]: strictly lower triangle only (zeros elsewhere); the diagonal goes to dg[]
-__device__ __forceinline__ void tf_load_diag(double* D, double* dg, const double* A, int ld, int kb, int nb, int tid) {
+// diagonal block -> shared [32][34]: lower triangle including the diagonal (zeros elsewhere)
+__device__ __forceinline__ void tf_load_diag(double* D, const double* A, int ld, int kb, int nb, int tid) {
   for (int e = tid; e < kFB * kFLD; e += kTailThreads) {
     const int i = e / kFLD, j = e % kFLD;
     double v = 0.0;
-    if (i < nb && j < i) v = A[(size_t)(kb + i) * ld + kb + j];
+    if (i < nb && j <= i) v = A[(size_t)(kb + i) * ld + kb + j];
     D[e] = v;
-  }
-  if (tid < kFB) dg[tid] = (tid < nb) ? A[(size_t)(kb + tid) * ld + kb + tid] : 1.0;
-}
-
-// One warp factorises a 32 x 32 block in place (lane = row, left-looking, strictly lower storage): column k of the factor
-// from the finished columns, 8 columns of the dot product per step.  decide(k, pivot) -> drop; inv[k] = 1 / L_kk (0 for a
-// dropped index, whose row and column leave the factor).  After pivot k, *step = k + 1 (followers poll it).
-#define TF_DSTAMP(i)                                                                   \
-  if (dprof && lane == 0 && k >= 20 && k < 22) {                                       \
-    unsigned long long t_;                                                             \
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory");                 \
-    dprof[6 * (k - 20) + (i)] = t_;                                                    \
-  }
-// Hand-off of per-pivot results between warps of one CTA through shared memory: the producer's lanes store their data,
-// __syncwarp() orders them before lane 0's volatile flag store; the consumer polls the flag, then reads the data.
-// Shared memory has no cache and a warp's shared-memory instructions are performed in issue order, so no MEMBAR is
-// needed (a __threadfence_block() per pivot costs ~113 cycles on each side, measured; the compiler barrier keeps the order).
-__device__ __forceinline__ void tf_publish(int* step, int v, int lane) {
-  __syncwarp();
-  if (lane == 0) *reinterpret_cast<volatile int*>(step) = v;
-}
-__device__ __forceinline__ void tf_wait(const int* step, int k) {
-  while (*reinterpret_cast<const volatile int*>(step) <= k) { }
-  asm volatile("" ::: "memory");
-}
-
-// One warp factorises a 32 x 32 block in place (lane = row i, strictly lower storage).  Left-looking with a one-pivot
-// look-ahead, so that only   shuffle -> FMA -> shuffle -> rsqrt -> multiply   sits on the dependent chain of a pivot:
-//   br_k(i) = a_ik - sum_{j<k-1} L_ij L_kj        is formed during pivot k-1 (it needs nothing pivot k-1 produces),
-//   t_i     = br_k(i) - L_{i,k-1} L_{k,k-1}       finishes column k with one FMA (L_{k,k-1} by shuffle from lane k),
-//   L_ik    = t_i / sqrt(t_k).
-// The loads and FMAs of br_{k+1} are independent of pivot k's rsqrt and sit in the same basic block, so the scheduler
-// overlaps them with it.  A row's slot of column k+1 is zeroed once its original value is in the bracket; together with
-// the strictly lower storage this makes every not-yet-final entry of a 16-column chunk read as zero: no masking.
-// decide(k, pivot) -> drop; inv[k] = 1 / L_kk (0 for a dropped index, whose row and column leave the factor).  After
-// pivot k, *step = k + 1 (followers poll it).
-template <class Decide>
-__device__ __forceinline__ void tf_factor(double* D, double dself, double* inv, int nb, int lane, int* step, Decide decide,
-                                          unsigned long long* dprof = nullptr) {
-  constexpr int LD = kFLD;
-  double* row = D + lane * LD;
-  double br = (lane == 0) ? dself : row[0];  // bracket of column 0: the original entry
-  if (lane > 0) row[0] = 0.0;
-  double lprev = 0.0;                        // this row's entry of the previous column
-  __syncwarp();
-  for (int k = 0; k < nb; ++k) {
-    TF_DSTAMP(0)
-    const double lk = __shfl_sync(0xffffffffu, lprev, k);  // L_{k,k-1}
-    const double t = br - lprev * lk;
-    const double pv = __shfl_sync(0xffffffffu, t, k);
-    TF_DSTAMP(1)
-    const bool drop = decide(k, pv);
-    TF_DSTAMP(2)
-    // ---- next bracket: loads first (before this pivot's stores), 16 columns per round trip, FMAs on 8 accumulators
-    const int k1 = (k + 1 < kFB) ? k + 1 : k;  // (the last pivot computes a dummy bracket)
-    const double* prow = D + k1 * LD;
-    const double anext = (lane == k1) ? dself : row[k1];
-    double a8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (16 * h < k) {
-        double p0[8], x0[8], p1[8], x1[8];
-        tf_ld8(prow + 16 * h, p0); tf_ld8(row + 16 * h, x0);
-        tf_ld8(prow + 16 * h + 8, p1); tf_ld8(row + 16 * h + 8, x1);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) a8[u] += x0[u] * p0[u];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) a8[u] += x1[u] * p1[u];
-      }
-    }
-    // ---- this pivot
-    const double iv = drop ? 0.0 : tf_rsqrt(pv);
-    const double lnew = (lane > k) ? t * iv : 0.0;
-    br = anext - (((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7])));
-    TF_DSTAMP(3)
-    if (lane > k && lane < nb) row[k] = lnew;
-    if (lane > k1) row[k1] = 0.0;                  // its original value lives in br now
-    if (drop && lane < k) D[k * LD + lane] = 0.0;  // a dropped index leaves the factor
-    if (lane == k) inv[k] = iv;
-    lprev = lnew;
-    TF_DSTAMP(4)
-    tf_publish(step, k + 1, lane);
-    TF_DSTAMP(5)
-  }
-}
-
-// One warp builds the inverse of the block's factor one pivot behind the factorising warp (lane = column c):
-// Linv[k][c] = (delta_kc - sum_{j<k} L[k][j] Linv[j][c]) / L[k][k]; a dropped pivot (1 / L_kk := 0) gives a zero row
-__device__ __forceinline__ void tf_invert(const double* Lf, const double* inv, double* LI, int nb, int lane, const int* step) {
-  constexpr int LD = kFLD;
-  for (int k = 0; k < nb; ++k) {
-    tf_wait(step, k);
-    double a8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {  // L's row k is zero from the diagonal on; 16 columns per round trip
-      if (16 * h < k) {
-        double p0[8], p1[8], y0[8], y1[8];
-        tf_ld8(Lf + k * LD + 16 * h, p0);
-        tf_ld8(Lf + k * LD + 16 * h + 8, p1);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { y0[u] = LI[(16 * h + u) * LD + lane]; y1[u] = LI[(16 * h + 8 + u) * LD + lane]; }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) a8[u] += p0[u] * y0[u];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) a8[u] += p1[u] * y1[u];
-      }
-    }
-    const double acc = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
-    const double ik = *reinterpret_cast<const volatile double*>(inv + k);
-    LI[k * LD + lane] = (lane <= k) ? ik * ((lane == k ? 1.0 : 0.0) - acc) : 0.0;
   }
 }
 
@@ -226,15 +103,15 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
   double* LIG = DA + NB * LD;                // [32][34] inverse of the factor of G's block
   double* LIA = LIG + NB * LD;               // [32][34] same for A
   double* WB = LIA + NB * LD;                // [32][34] the current block of this CTA's W rows
-  double* PT_A = WB + NB * LD;               // [32][ldt] panel of A, transposed
+  double* DT = WB + NB * LD;                 // [32][34] scratch of the diagonal block's inverse (CTA 0)
+  double* PT_A = DT + NB * LD;               // [32][ldt] panel of A, transposed
   double* PT_G = PT_A + (size_t)NB * ldt;    // [32][ldt] panel of G, transposed
   double* Ws = PT_G + (size_t)NB * ldt;      // [32][ldt] row c = RHS column col0 + c of the substitution
   double* XT = Ws + (size_t)NB * ldt;        // [32][32]  solved block of the W rows, transposed
   double* d0 = XT + NB * NB;                 // [n] original diagonal of Gamma (CTA 0)
   double* idg = d0 + ((n + 1) & ~1);         // [32] 1 / diag of the block's factor of G (0 = dropped)
   double* ida = idg + NB;                    // [32] same for A
-  __shared__ double dgG[NB], dgA[NB];        // diagonals of the current blocks
-  __shared__ int s_rankA, s_rankG, s_stepA, s_stepG;
+  __shared__ int s_rankA, s_rankG;
   const int m = *m_in;
   const bool full = m <= n;  // all rows explicit and orthonormal: Gamma = I_m, nothing to decide, G untouched
   const int rank_cap = min(m, n);
@@ -279,40 +156,12 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
   // other CTAs run the trailing update of block kb (it only needs the leading 32 x 32 tile of that update, which CTA 0
   // forms itself from the panel).
   auto factor_block = [&](int kb, int nb, bool stamps) {
-    for (int e = tid; e < NB * LD; e += kTailThreads) { LIA[e] = 0.0; LIG[e] = 0.0; }
-    if (tid == 0) { s_stepA = 0; s_stepG = 0; }
-    __syncthreads();
     if (stamps && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[76] = t_; }
-    if (warp == 3 && !full) {
-      int rk = s_rankG;
-      tf_factor(DG, dgG[lane], idg, nb, lane, &s_stepG, [&](int k, double pv) {
-        const double dk0 = d0[kb + k];
-        const bool drop = !(dk0 > 0.0) || !(pv > thr * dk0) || rk >= rank_cap;
-        if (!drop) rk++;
-        return drop;
-      });
-      if (lane == 0) s_rankG = rk;
-    } else if (warp == 0) {
-      int rk = s_rankA;
-      tf_factor(DA, dgA[lane], ida, nb, lane, &s_stepA, [&](int k, double pv) {
-        bool drop;
-        if (full) drop = !(d0[kb + k] > 0.0) || rk >= rank_cap;
-        else {
-          tf_wait(&s_stepG, k);
-          drop = *reinterpret_cast<volatile double*>(idg + k) == 0.0;
-        }
-        drop = drop || !(pv > 0.0);
-        if (!drop) rk++;
-        return drop;
-      }, stamps ? prof + 64 : nullptr);
-      if (lane == 0) s_rankA = rk;
-      for (int k = nb + lane; k < NB; k += 32) { ida[k] = 0.0; idg[k] = 0.0; }
-    } else if (warp == 1) {
-      tf_invert(DA, ida, LIA, nb, lane, &s_stepA);
-    } else if (warp == 2 && !full) {
-      tf_invert(DG, idg, LIG, nb, lane, &s_stepG);
-    }
+    TfRank rk;
+    rk.g = s_rankG; rk.a = s_rankA;
     __syncthreads();
+    rk = tf_factor_block(DG, DA, LIG, LIA, idg, ida, d0, kb, nb, thr, rank_cap, full, rk, tid, kTailThreads, WB, DT, stamps ? prof + 60 : nullptr);
+    if (tid == 0) { s_rankG = rk.g; s_rankA = rk.a; }
     if (stamps && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[77] = t_; }
     // the inverses go to the other CTAs through L2 (a DSMEM push of 2 x 8.7 KB to 7 CTAs runs at ~20 B/clk: 3 us)
     for (int e = tid; e < NB * LD / 2; e += kTailThreads) {
@@ -322,8 +171,9 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
   };
   if (crank == 0) {
     const int nb0 = min(NB, n);
-    if (!full) tf_load_diag(DG, dgG, G, ld, 0, nb0, tid);
-    tf_load_diag(DA, dgA, A, ld, 0, nb0, tid);
+    if (!full) tf_load_diag(DG, G, ld, 0, nb0, tid);
+    tf_load_diag(DA, A, ld, 0, nb0, tid);
+    __syncthreads();
     factor_block(0, nb0, prof != nullptr);
   }
   stamp();  // diagonal block 0 done
@@ -455,10 +305,10 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
           va = A[(size_t)(r0 + i) * ld + r0 + j] - sa;
           if (!full) vg = G[(size_t)(r0 + i) * ld + r0 + j] - sg;
         }
-        if (j == i && i < NB) { dgA[i] = (i < nb2) ? va : 1.0; dgG[i] = (i < nb2) ? vg : 1.0; va = 0.0; vg = 0.0; }
         DA[e] = va;
         DG[e] = vg;
       }
+      __syncthreads();
       factor_block(r0, nb2, false);
     } else {
       const int nt = (nr + 3) / 4, ntile = nt * (nt + 1) / 2;

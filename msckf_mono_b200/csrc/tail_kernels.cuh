@@ -114,7 +114,10 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_s(const UpdArgs<S>* __res
               [&](int a, int b, double v) { S2[(size_t)a * ld + b] = v + R2[(size_t)a * ld + b]; });
 }
 
-// P <- P - W^T W (lower-triangular tile pairs; written in the filter precision, exactly symmetric by construction)
+// P <- P - W^T W (lower-triangular tile pairs; written in the filter precision, exactly symmetric by construction), and in
+// the same launch  dx = W^T y  (the CTAs of the first tile column each take 32 components) followed by the state injection of
+// msckf.h:1373-1391 by whichever CTA finishes last (ticket counter) -- round 1 ran both as a separate single-CTA kernel
+// (k_inject: 20 us for a 195 x 195 mat-vec).
 template <class S>
 __global__ void __launch_bounds__(kGemmThreads) k_syrk(const UpdArgs<S>* __restrict__ args) {
   pdl_wait();
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(kGemmThreads) k_syrk(const UpdArgs<S>* __restr
   if ((int)blockIdx.x >= nt32 * (nt32 + 1) / 2 || A.n_tracks == 0) return;
   const double* __restrict__ Wm = A.W;
   S* __restrict__ P = A.P;
-  if (*A.m_out == 0) return;
+  if (*A.m_out == 0) return;  // nothing accepted: the reference returns before touching the state (msckf.h:401-403, :1328)
   int pidx = blockIdx.x, ta = 0;
   while (pidx >= ta + 1) { pidx -= ta + 1; ++ta; }  // (ta >= tb)
   const int tb = pidx;
@@ -140,6 +143,73 @@ __global__ void __launch_bounds__(kGemmThreads) k_syrk(const UpdArgs<S>* __restr
                   P[(size_t)b * ldp + a] = r;
                 }
               });
+  const int tid = threadIdx.x;
+  __shared__ double part[kGemmThreads / 32][33];
+  __shared__ int s_last;
+  if (tb == 0) {  // dx[a] = sum_k W[k][a] y[k] for the 32 components of this tile row
+    const int al = tid & 31, kg = tid >> 5, a = ta * 32 + al;
+    const double* __restrict__ yv = A.y;
+    double s = 0.0;
+    if (a < n)
+      for (int k = kg; k < n; k += kGemmThreads / 32) s += Wm[(size_t)k * ld + a] * yv[k];
+    part[kg][al] = s;
+    __syncthreads();
+    if (kg == 0 && a < n) {
+      double t = 0.0;
+#pragma unroll
+      for (int g = 0; g < kGemmThreads / 32; ++g) t += part[g][al];
+      A.dx[a] = t;
+    }
+  }
+  // ---- the last CTA injects the correction (msckf.h:1373-1391)
+  __syncthreads();
+  if (tid == 0) { __threadfence(); s_last = (atomicAdd(A.done, 1u) == (unsigned)(nt32 * (nt32 + 1) / 2) - 1u) ? 1 : 0; }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  DevState<S>* st = A.st;
+  S* __restrict__ poses = A.poses;
+  const double* dx = A.dx;
+  if (tid == 0) {
+    *A.done = 0u;
+    const S dth[3] = {(S)__ldcg(dx + 0), (S)__ldcg(dx + 1), (S)__ldcg(dx + 2)};
+    S uq[4], qn[4];
+    build_update_quat(dth, uq);
+    quat_mul(uq, st->q_IG, qn);  // not renormalised (msckf.h:1376-1378)
+    for (int i = 0; i < 4; ++i) st->q_IG[i] = qn[i];
+    for (int i = 0; i < 3; ++i) {
+      st->b_g[i] += (S)__ldcg(dx + 3 + i);
+      st->v_I_G[i] += (S)__ldcg(dx + 6 + i);
+      st->b_a[i] += (S)__ldcg(dx + 9 + i);
+      st->p_I_G[i] += (S)__ldcg(dx + 12 + i);
+    }
+    st->n_updates += 1;
+    st->last_m = A.m_out[0];
+    st->last_rank = *A.rank_out;
+  }
+  double nn = 0.0;
+  for (int a = tid; a < n; a += kGemmThreads) { const double v = __ldcg(dx + a); nn += v * v; }
+  nn = warp_sum(nn);
+  __syncthreads();
+  if ((tid & 31) == 0) part[0][tid >> 5] = nn;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kGemmThreads / 32; ++w) t += part[0][w];
+    st->last_dx_norm = sqrt(t);
+    if (!isfinite(t)) A.m_out[2] = 1;  // non-finite delta-x
+    st->last_status = A.m_out[2];
+  }
+  for (int ci = tid; ci < A.M; ci += kGemmThreads) {
+    S* ps = poses + kPoseStride * ci;
+    const S dth[3] = {(S)__ldcg(dx + 15 + 6 * ci), (S)__ldcg(dx + 16 + 6 * ci), (S)__ldcg(dx + 17 + 6 * ci)};
+    S uq[4], qn[4];
+    build_update_quat(dth, uq);
+    quat_mul(uq, ps, qn);
+    quat_normalize(qn);
+    ps[0] = qn[0]; ps[1] = qn[1]; ps[2] = qn[2]; ps[3] = qn[3];
+    ps[4] += (S)__ldcg(dx + 18 + 6 * ci); ps[5] += (S)__ldcg(dx + 19 + 6 * ci); ps[6] += (S)__ldcg(dx + 20 + 6 * ci);
+  }
 }
 
 }  // namespace mb

@@ -12,7 +12,7 @@ sys.path.insert(0, str(ROOT))
 from msckf_mono_b200 import capi, engine_filter, synth  # noqa: E402
 
 
-def table(nf, nc, dtype, reps=6):
+def table(nf, nc, dtype, reps=6, options=()):
     wl = synth.make_window_workload(n_features=nf, n_clones=nc, seq=30)
     caps = dict(max_clones=nc + 8, max_tracks=max(512, nf + 48), max_obs=max(512, nf + 48) * nc)
     f = engine_filter(dtype, **caps)
@@ -21,6 +21,8 @@ def table(nf, nc, dtype, reps=6):
     batch = capi.TrackBatch(off, obs, idx, dtype)
     tmpl = capi.Engine(dtype, borrowed=f.engineHandle())
     work = capi.Engine(dtype, **caps)
+    for key, val in options:
+        work.set_option(key, val)
     tot = []
     for _ in range(reps):
         work.copy_state_from(tmpl)
@@ -45,4 +47,7 @@ def table(nf, nc, dtype, reps=6):
 if __name__ == "__main__":
     nf, nc = int(sys.argv[1]), int(sys.argv[2])
     dtype = np.float64 if sys.argv[3] == "f64" else np.float32
-    print(json.dumps(table(nf, nc, dtype)))
+    opts = [(int(a.split("=")[0]), float(a.split("=")[1])) for a in sys.argv[4:]]
+    out = table(nf, nc, dtype, options=opts)
+    out["options"] = opts
+    print(json.dumps(out))

@@ -151,6 +151,7 @@ int msckf_b200_get_covariance(msckf_b200_engine* e, void* out) {
   std::memset(out, 0, (size_t)n * n * (e->dtype == MSCKF_B200_F32 ? 4 : 8));
   return n;
 }
+int msckf_b200_set_covariance(msckf_b200_engine*, const void*) { return 0; }
 int msckf_b200_get_counters(msckf_b200_engine* e, long long* c) { for (int i = 0; i < 8; ++i) c[i] = 0; c[3] = e->updates; return 0; }
 int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap) {
   const int n = 15 + 6 * e->M;

@@ -1,97 +1,62 @@
 """GPU parity tests: the B200 engine behind the MSCKF<_S> surface (through the C view / C-ABI of
 libmsckf_b200.so) against the CPU oracle on identical seeded inputs.
 
-Tolerances (stated per test):
-  * integer bookkeeping (valid / accepted flags, clone ids, tracked ids, counters): bit-exact;
-  * fp64 vs the oracle's implementation-independent part (drop_null_rows): tight (<= 1e-6 relative on dx);
-  * fp64 vs the reference-faithful oracle: dx within 1e-3 relative -- the reference keeps rows of T_H that
-    come from numerically zero pivots; their Q_1 columns are rounding noise and move dx
-    by ~1e-5..1e-4 relative on these workloads, for ANY implementation (incl. Eigen vs LAPACK);
-  * fp32: the triangulation is ill-conditioned enough that two fp32 implementations differ by 1e-3..1e-1
-    relative on dx; the engine must be as close to the fp64 oracle as the fp32 oracle is (factor 4).
+What is asserted:
+  * integer bookkeeping (valid / accepted flags = zero accept/reject flips, clone ids, tracked ids, counters): bit-exact,
+    inside every case (tests/parity_cases.py);
+  * every floating-point difference against 10 x its committed measurement (tests/golden/parity_measured.json, written by
+    scripts/measure_parity.py on the B200): no hand-picked loose bounds -- a regression of more than one decade fails;
+  * on top of that the contract tolerances of SURVEY.md 8d where the path meets them: fp64 vs the oracle's implementation-
+    independent part (exact-subspace mode) <= 1e-9 relative on small windows; trajectory RMS < 1e-4 m.
+The oracle modes: `clean` = exact subspace (drop_null_rows), `faithful` = reference-literal compression (its rows from
+numerically zero pivots are rounding noise), fp32 cases compare the fp32 engine with the fp32 oracle DIRECTLY.
 """
 import numpy as np
 import pytest
 
-from tests.common import GOLDEN, make_oracle, quat_err, rel, run_collect, state_of, synth
+from tests import parity_cases as pc
+from tests.common import make_oracle, rel, run_collect, synth
+from tests.parity_cases import make_engine
 
 pytestmark = pytest.mark.gpu
 
 
-def make_engine(dtype, **kw):
-    from msckf_mono_b200 import engine_filter
-    return engine_filter(dtype, **kw)
-
-
-WINDOWS = [(3, 4, 5), (8, 6, 3), (40, 12, 4), (300, 30, 0)]
-
-
-def _drive_pair(g, o, wl, **kw):
-    rg = run_collect(g, wl, **kw)
-    ro = run_collect(o, wl, **kw)
-    return rg, ro
-
-
-def _assert_bookkeeping_equal(g, o, rg, ro):
-    assert np.array_equal(rg["ntracks"], ro["ntracks"])
-    assert np.array_equal(rg["valid"], ro["valid"])
-    assert np.array_equal(rg["accepted"], ro["accepted"])
-    sg, so = state_of(g), state_of(o)
-    for k in ("cam_ids", "cam_last_corr", "tracked_ids"):
-        assert np.array_equal(sg[k], so[k]), k
-    assert np.array_equal(g.getPrunedStates()["state_id"], o.getPrunedStates()["state_id"])
-    cg, co = g.counters(), o.counters()
-    for k in ("num_residualized", "pfg_shifted", "pfg_oob", "n_updates"):
-        assert cg[k] == co[k], (k, cg, co)
-    return sg, so
-
-
-@pytest.mark.parametrize("nf,nc,seq", WINDOWS)
+@pytest.mark.parametrize("nf,nc,seq", pc.WINDOWS)
 def test_window_fp64_vs_clean_oracle(oracle_lib, nf, nc, seq):
-    wl = synth.make_window_workload(n_features=nf, n_clones=nc, seq=seq)
-    g, o = make_engine(np.float64), make_oracle(oracle_lib, np.float64, drop_null_rows=True)
-    rg, ro = _drive_pair(g, o, wl)
-    sg, so = _assert_bookkeeping_equal(g, o, rg, ro)
-    rep_g, rep_o = g.lastReport(), o.lastReport()
-    assert rel(rep_g["gamma"], rep_o["gamma"]) < 1e-8
-    assert rel(rep_g["p_f_G"], rep_o["p_f_G"]) < 1e-6
-    assert rel(g.lastDeltaX(), o.lastDeltaX()) < 1e-6
-    assert np.abs(sg["P"] - so["P"]).max() / np.abs(so["P"]).max() < 1e-7
-    assert np.abs(sg["imu_p"] - so["imu_p"]).max() < 1e-7 and np.abs(sg["cam_p"] - so["cam_p"]).max() < 1e-7
-    assert quat_err(sg["imu_q"], so["imu_q"]) < 2e-7 and quat_err(sg["cam_q"], so["cam_q"]) < 2e-7
-    assert g.counters()["rows_kept"] == o.counters()["rows_kept"]  # same rank decision
+    name = f"f64_clean_{nf}x{nc}"
+    got = pc.check(name, pc.run_case(name))
+    assert got["rank_engine"] == got["rank_oracle"]  # same rank decision
+    if nf <= 40:  # the contract tolerance of SURVEY 8d (fp64 <= 1e-9) holds outright on the small windows
+        assert got["dx"] < 1e-9 and got["P"] < 1e-9 and got["gamma"] < 1e-9
 
 
-@pytest.mark.parametrize("nf,nc,seq", WINDOWS)
+@pytest.mark.parametrize("nf,nc,seq", pc.WINDOWS)
 def test_window_fp64_vs_reference_faithful_oracle(oracle_lib, nf, nc, seq):
-    wl = synth.make_window_workload(n_features=nf, n_clones=nc, seq=seq)
-    g, o = make_engine(np.float64), make_oracle(oracle_lib, np.float64, faithful_max_rows=900)
-    rg, ro = _drive_pair(g, o, wl)
-    sg, so = _assert_bookkeeping_equal(g, o, rg, ro)
-    assert rel(g.lastDeltaX(), o.lastDeltaX()) < 1e-3
-    assert np.abs(sg["P"] - so["P"]).max() / np.abs(so["P"]).max() < 1e-6
-    assert np.abs(sg["imu_p"] - so["imu_p"]).max() < 1e-5
+    name = f"f64_faithful_{nf}x{nc}"
+    pc.check(name, pc.run_case(name))
+
+
+@pytest.mark.parametrize("nf,nc,seq", pc.WINDOWS)
+def test_window_fp32_engine_vs_fp32_oracle_direct(oracle_lib, nf, nc, seq):
+    """the fp32 engine against the fp32 oracle on identical float32 inputs: flips = 0 (inside the case), dx / P / gamma / p_f_G"""
+    name = f"f32_direct_{nf}x{nc}"
+    pc.check(name, pc.run_case(name))
 
 
 def test_isotropic_noise_makes_null_rows_irrelevant(oracle_lib):
     """f_u == f_v => R_n = sigma^2 I: any basis of the subspace gives the reference result to rounding."""
-    wl = synth.make_window_workload(n_features=40, n_clones=12, seq=4, isotropic=True)
-    g, o = make_engine(np.float64), make_oracle(oracle_lib, np.float64)
-    rg, ro = _drive_pair(g, o, wl)
-    _assert_bookkeeping_equal(g, o, rg, ro)
-    assert rel(g.lastDeltaX(), o.lastDeltaX()) < 1e-7
-    assert rel(g.getCovariance(), o.getCovariance()) < 1e-8
+    got = pc.check("f64_iso_40x12", pc.run_case("f64_iso_40x12"))
+    assert got["dx"] < 1e-9 and got["P"] < 1e-9
 
 
-@pytest.mark.parametrize("nf,nc,seq", WINDOWS)
+@pytest.mark.parametrize("nf,nc,seq", pc.WINDOWS)
 def test_window_fp32_as_close_to_fp64_truth_as_fp32_oracle(oracle_lib, nf, nc, seq):
+    """second view of the fp32 path: its distance to the fp64 truth is the fp32 oracle's own distance (factor 4)"""
     wl = synth.make_window_workload(n_features=nf, n_clones=nc, seq=seq)
     g = make_engine(np.float32)
     o32 = make_oracle(oracle_lib, np.float32)
     o64 = make_oracle(oracle_lib, np.float64, drop_null_rows=True)
-    # identical (float32-rounded) inputs for all three
-    for f in (g, o32, o64):
-        f._round = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+    pc.f32_inputs(g, o32, o64)
     rg = run_collect(g, wl)
     r32 = run_collect(o32, wl)
     run_collect(o64, wl)
@@ -103,90 +68,68 @@ def test_window_fp32_as_close_to_fp64_truth_as_fp32_oracle(oracle_lib, nf, nc, s
     eP_g = np.abs(g.getCovariance() - P64).max() / np.abs(P64).max()
     eP_o = np.abs(o32.getCovariance() - P64).max() / np.abs(P64).max()
     assert eP_g < 4 * eP_o + 1e-5, (eP_g, eP_o)
-    p64 = o64.getImuState()["p_I_G"]
-    assert np.abs(g.getImuState()["p_I_G"] - p64).max() < 4 * np.abs(o32.getImuState()["p_I_G"] - p64).max() + 1e-5
+
+
+@pytest.mark.parametrize("mode", ["clean", "faithful"])
+def test_config_s_shape_500x60_fp64_vs_oracle_fixture(mode):
+    """BASELINE config-S shape (n = 375: the non-fused tail kernel, the fp64 k_jac without the single-warp gate copy) against
+    the committed outputs of the oracle (which needs a minute of CPU here): zero flips, numbers vs measurement."""
+    name = f"stress_f64_500x60_{mode}"
+    got = pc.check(name, pc.run_case(name))
+    assert got["m"] == 500 * 117
+    if mode == "clean":
+        assert got["rank_engine"] == got["rank_oracle"]
+
+
+@pytest.mark.parametrize("mode", ["clean", "faithful"])
+def test_config_s_full_2000x60_fp64_vs_oracle_fixture(mode):
+    """the full BASELINE config S (2000 features x 60 clones, fp64; the oracle needs 4 minutes of CPU: committed fixture)"""
+    name = f"stress_f64_2000x60_{mode}"
+    got = pc.check(name, pc.run_case(name))
+    assert got["m"] == 2000 * 117 and got["flips"] == 0
+
+
+@pytest.mark.parametrize("mode", ["clean", "faithful"])
+def test_config_b_fp32_vs_oracle_fixture(mode):
+    name = f"configB_f32_300x30_{mode}"
+    got = pc.check(name, pc.run_case(name))
+    assert got["m"] == 300 * 57 and got["flips"] == 0
 
 
 @pytest.mark.parametrize("name", ["win_f64_8x6_clean", "win_f64_40x12_clean", "win_f64_iso_40x12", "win_f64_3x4", "stream_f64_60"])
 def test_engine_matches_numpy_golden(name):
     """engine vs the committed fixtures of the independent NumPy/LAPACK restatement (no oracle involved)."""
-    from tests.golden.make_golden import CASES, make_workload
-    kind, kw, dtype, drop = CASES[name]
-    gold = np.load(GOLDEN / f"{name}.npz")
-    g = make_engine(np.dtype(dtype))
-    rec = run_collect(g, make_workload(kind, kw))
-    st = state_of(g)
-    assert np.array_equal(rec["valid"], gold["all_valid"]) and np.array_equal(rec["accepted"], gold["all_accepted"])
-    assert np.array_equal(st["cam_ids"], gold["cam_ids"]) and np.array_equal(st["tracked_ids"], gold["tracked_ids"])
-    assert np.abs(st["P"] - gold["P"]).max() / np.abs(gold["P"]).max() < 1e-7
-    assert np.abs(st["imu_p"] - gold["imu_p"]).max() < 1e-7
-    assert quat_err(st["cam_q"], gold["cam_q"]) < 1e-7
+    pc.check(f"numpy_{name}", pc.run_case(f"numpy_{name}"))
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_stream_bookkeeping_bit_exact(oracle_lib, dtype):
-    """E-sim: 150 frames of propagate / augment / update / addFeatures / marginalize / pruneEmptyStates."""
-    wl = synth.make_stream_workload(n_frames=150, seq=7, max_features=40, max_track_length=14, max_cam_states=12)
-    g, o = make_engine(dtype), make_oracle(oracle_lib, dtype, drop_null_rows=(dtype == np.float64))
-    rg, ro = _drive_pair(g, o, wl)
-    sg, so = _assert_bookkeeping_equal(g, o, rg, ro)
-    assert g.counters()["n_updates"] > 60
-    # 100+ chained updates: differences accumulate through the filter dynamics
-    tol = 1e-5 if dtype == np.float64 else 5e-3
-    assert np.abs(sg["imu_p"] - so["imu_p"]).max() < tol
-    assert np.abs(sg["P"] - so["P"]).max() / np.abs(so["P"]).max() < (1e-5 if dtype == np.float64 else 2e-2)
-    for cam in range(g.getNumCamStates()):
-        assert np.array_equal(g.getCamTrackedIds(cam), o.getCamTrackedIds(cam))
+    name = f"stream150_{np.dtype(dtype).name}"
+    pc.check(name, pc.run_case(name))
 
 
-def test_stream_trajectory_rms_vs_oracle_fp64(oracle_lib):
-    """north-star trajectory bar: RMS position difference engine vs oracle < 1e-4 m over the sequence."""
-    wl = synth.make_stream_workload(n_frames=200, seq=8, max_features=60, max_track_length=20, max_cam_states=20)
-    wl["noise"] = synth.euroc_noise(tuned=True)
-    g, o = make_engine(np.float64), make_oracle(oracle_lib, np.float64)
-    pg, po = [], []
-    synth.drive(g, wl, on_frame=lambda k, f: pg.append(f.getImuState()["p_I_G"].copy()))
-    synth.drive(o, wl, on_frame=lambda k, f: po.append(f.getImuState()["p_I_G"].copy()))
-    d = np.array(pg) - np.array(po)
-    rms = np.sqrt((d ** 2).sum(axis=1).mean())
-    assert rms < 1e-4, rms
-    truth = np.array([wl["traj"].pos(fr["time"]) for fr in wl["frames"]])
-    assert np.sqrt(((np.array(pg) - truth) ** 2).sum(axis=1).mean()) < 0.1
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_stream_trajectory_rms_vs_oracle(oracle_lib, dtype):
+    """north-star trajectory bar: RMS position difference engine vs oracle < 1e-4 m over the sequence (fp64 and fp32)"""
+    name = f"traj200_{np.dtype(dtype).name}"
+    got = pc.check(name, pc.run_case(name))
+    assert got["rms_m"] < 1e-4, got
+    assert got["rms_vs_truth_m"] < 0.1
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_prune_redundant_states(oracle_lib, dtype):
     """pruneRedundantStates (msckf.h:453-682): TRIANGULATE + RESIDUALIZE entry points and the covariance gather."""
-    wl = synth.make_stream_workload(n_frames=90, seq=9, max_features=40, max_track_length=40, max_cam_states=21)
-    # slow the keyframe criterion down so clones are actually declared redundant
-    wl["params"]["redundancy_angle_thresh"] = 0.2
-    wl["params"]["redundancy_distance_thresh"] = 0.2
-    g, o = make_engine(dtype), make_oracle(oracle_lib, dtype, drop_null_rows=(dtype == np.float64))
-    rg, ro = _drive_pair(g, o, wl, prune_redundant=True)
-    sg, so = _assert_bookkeeping_equal(g, o, rg, ro)
-    assert len(g.getPrunedStates()["state_id"]) > 10
-    tol = 1e-5 if dtype == np.float64 else 2e-2
-    assert np.abs(sg["P"] - so["P"]).max() / np.abs(so["P"]).max() < tol
-    assert np.abs(sg["imu_p"] - so["imu_p"]).max() < (1e-5 if dtype == np.float64 else 5e-3)
+    name = f"prune_redundant_{np.dtype(dtype).name}"
+    pc.check(name, pc.run_case(name))
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_rejections_and_pfg_index_quirk(oracle_lib, dtype):
     """outliers (LM cost / cheirality / chi-square gate) and checkMotion rejections, including the reference's
     p_f_G_vec mis-indexing after a checkMotion rejection (msckf.h:357 vs :374 vs :419)."""
-    wl = synth.make_window_workload(n_features=120, n_clones=10, seq=12)
-    synth.corrupt_observations(wl, seed=3)
-    wl["params"]["translation_threshold"] = 0.2  # between the features' orthogonal translations
-    g, o = make_engine(dtype), make_oracle(oracle_lib, dtype, drop_null_rows=(dtype == np.float64))
-    rg, ro = _drive_pair(g, o, wl)
-    rep = g.lastReport()
-    assert 0 < rep["cm_passed"].sum() < len(rep["cm_passed"])           # some checkMotion rejections ...
-    assert 0 < rep["accepted"].sum() < rep["valid"].sum()              # ... some gate rejections
-    sg, so = _assert_bookkeeping_equal(g, o, rg, ro)
-    assert g.counters()["pfg_shifted"] > 0
-    assert np.array_equal(rep["cm_passed"], o.lastReport()["cm_passed"])
-    tol = 1e-6 if dtype == np.float64 else 5e-2
-    assert rel(g.lastDeltaX(), o.lastDeltaX()) < tol
+    name = f"rejections_{np.dtype(dtype).name}"
+    pc.check(name, pc.run_case(name))
 
 
 def test_no_accepted_track_leaves_state_untouched(oracle_lib):
@@ -204,16 +147,7 @@ def test_no_accepted_track_leaves_state_untouched(oracle_lib):
 
 
 def test_finish_residualises_remaining_tracks(oracle_lib):
-    wl = synth.make_stream_workload(n_frames=25, seq=14, max_features=30, max_track_length=40, max_cam_states=30)
-    g, o = make_engine(np.float64), make_oracle(oracle_lib, np.float64, drop_null_rows=True)
-    synth.drive(g, wl)
-    synth.drive(o, wl)
-    g.finish()
-    o.finish()
-    rg, ro = g.lastReport(), o.lastReport()
-    assert len(rg["valid"]) > 10 and np.array_equal(rg["valid"], ro["valid"]) and np.array_equal(rg["accepted"], ro["accepted"])
-    assert rel(g.getCovariance(), o.getCovariance()) < 1e-7
-    assert len(g.getMap()) == len(o.getMap()) and rel(g.getMap(), o.getMap()) < 1e-6
+    pc.check("finish", pc.run_case("finish"))
 
 
 def test_handles_are_independent():
@@ -246,21 +180,13 @@ def test_handles_are_independent():
 def test_fused_and_separate_substitution_agree(nf, nc, seq):
     """The tail kernel runs the forward substitution either fused into the blocked Cholesky (default where the window
     fits) or as a separate sweep (large windows; engine option 3 = 0): same factor, same results up to rounding."""
-    wl = synth.make_window_workload(n_features=nf, n_clones=nc, seq=seq)
-    a, b = make_engine(np.float64), make_engine(np.float64)
-    synth.drive(a, wl, marginalize_last=False)
-    synth.drive(b, wl, marginalize_last=False)
-    b.setOption(103, 0.0)
-    a.marginalize(); b.marginalize()
-    assert a.counters()["rows_kept"] == b.counters()["rows_kept"]
-    # the fused form solves the panels through the explicit inverse of each 32 x 32 diagonal block: errors grow with the
-    # block's condition number instead of staying backward stable, hence 1e-7 / 1e-8 here (both are 1e-6-close to the oracle)
-    ddx = rel(a.lastDeltaX(), b.lastDeltaX())
-    Pa, Pb = a.getCovariance(), b.getCovariance()
-    dP = np.abs(Pa - Pb).max() / np.abs(Pa).max()
-    print(f"fused vs separate substitution: dx rel {ddx:.3e}, P rel {dP:.3e}")
-    assert ddx < 1e-7, ddx
-    assert dP < 1e-8, dP
+    name = f"fused_vs_separate_{nf}x{nc}"
+    pc.check(name, pc.run_case(name))
+
+
+def test_gram_on_fp64_tensor_cores_matches_simt_tiles():
+    """engine option 5: the compression's Gram products as DMMA (mma.sync m8n8k4 f64) vs SIMT DFMA tiles -- same rank, same flags"""
+    pc.check("gram_mma_vs_simt_300x30", pc.run_case("gram_mma_vs_simt_300x30"))
 
 
 def test_batched_entry_point_matches_individual_updates():
@@ -370,52 +296,49 @@ def test_c_abi_update_batch_matches_separate_updates():
 
 def test_maximum_track_length_98_fp64(oracle_lib):
     """The reference's chi-square table has 99 entries (msckf.h:91), so 98 observations per track is the longest track it
-    can gate.  98 clones -> n = 603: the large-window tail kernel (blocks of 16) and the CTA-wide gate (the single-warp
-    copy does not fit next to a 196 x 196 packed matrix in fp64) -- paths the other tests do not reach."""
-    wl = synth.make_window_workload(n_features=24, n_clones=98, seq=11, imu_per_frame=2)  # 10 ms frames: everything stays in view
-    g = make_engine(np.float64, max_clones=104, max_tracks=64, max_obs=64 * 98)
-    o = make_oracle(oracle_lib, np.float64, drop_null_rows=True)
-    rg, ro = _drive_pair(g, o, wl)
-    sg, so = _assert_bookkeeping_equal(g, o, rg, ro)
-    rep_g, rep_o = g.lastReport(), o.lastReport()
-    assert rep_g["rows"].max() == 2 * 98 - 3
-    ddx = rel(g.lastDeltaX(), o.lastDeltaX())
-    dP = np.abs(sg["P"] - so["P"]).max() / np.abs(so["P"]).max()
-    print(f"L = 98, n = 603: dx rel {ddx:.2e}, P rel {dP:.2e}, gamma rel {rel(rep_g['gamma'], rep_o['gamma']):.2e}, rows kept {g.counters()['rows_kept']}")
-    assert rel(rep_g["gamma"], rep_o["gamma"]) < 1e-7
-    assert ddx < 1e-5 and dP < 1e-6
+    can gate.  98 clones -> n = 603: the large-window tail kernel (blocks of 16) and the CTA-wide gate -- paths the other
+    tests do not reach."""
+    got = pc.check("l98_f64", pc.run_case("l98_f64"))
     # 7 gauge directions; one of them is only nearly null at this geometry, and the two implementations' thresholds
     # (pivot of the basis Gram matrix vs. a pivoted QR) land on either side of it -- with no effect on the result above
-    assert o.counters()["rows_kept"] in (603 - 7, 603 - 6) and g.counters()["rows_kept"] in (603 - 7, 603 - 6)
+    assert got["rank_oracle"] in (603 - 7, 603 - 6) and got["rank_engine"] in (603 - 7, 603 - 6)
 
 
 def test_engine_update_is_invariant_to_track_order():
     """Same property as tests/test_oracle.py::test_update_is_invariant_to_track_order, on the engine alone (isotropic
     pixel noise): permuting the features permutes the per-track outputs and leaves the update unchanged."""
-    from tests.test_oracle import _permuted
-    wl = synth.make_window_workload(n_features=40, n_clones=12, seq=22, isotropic=True)
-    perm = np.random.default_rng(22).permutation(40)
-    a, b = make_engine(np.float64), make_engine(np.float64)
-    ra, rb = run_collect(a, wl), run_collect(b, _permuted(wl, perm))
-    assert ra["valid"].all() and np.array_equal(np.asarray(ra["accepted"])[perm], rb["accepted"])
-    ddx = rel(a.lastDeltaX(), b.lastDeltaX())
-    Pa, Pb = a.getCovariance(), b.getCovariance()
-    dP = np.abs(Pa - Pb).max() / np.abs(Pa).max()
-    print(f"engine order invariance: dx rel {ddx:.2e}, P rel {dP:.2e}")
-    assert ddx < 1e-6 and dP < 1e-8
-    assert rel(np.asarray(a.lastReport()["gamma"])[perm], b.lastReport()["gamma"]) < 1e-9
+    pc.check("order_invariance", pc.run_case("order_invariance"))
+
+
+def test_non_finite_update_is_reported_not_hidden():
+    """MSCKF_B200_ERR_NUMERIC: a covariance poisoned with NaN makes the update non-finite; the engine applies it like the
+    reference would (msckf.h:1369-1418 has no check) and says so through the fetch status."""
+    from msckf_mono_b200 import capi
+    wl = synth.make_window_workload(n_features=12, n_clones=6, seq=13)
+    f = make_engine(np.float64)
+    synth.drive(f, wl, marginalize_last=False)
+    off, obs, idx = f.packQueued()
+    e = capi.Engine(np.float64, borrowed=f.engineHandle())
+    ok = capi.Engine(np.float64)
+    ok.copy_state_from(e)
+    assert ok.update(capi.MARGINALIZE, capi.TrackBatch(off, obs, idx, np.float64))["m"] > 0
+    bad = capi.Engine(np.float64)
+    bad.copy_state_from(e)
+    bad.poison_covariance()
+    with pytest.raises(RuntimeError, match="non-finite"):
+        bad.update(capi.MARGINALIZE, capi.TrackBatch(off, obs, idx, np.float64))
 
 
 def test_full_size_properties_stress_fp64():
-    """BASELINE config S (2000 features x 60 clones, fp64): size-independent properties (the oracle would take
-    minutes here): exact symmetry, positive semi-definiteness, information gain, rank = n - 7 gauge directions."""
+    """BASELINE config S (2000 features x 60 clones, fp64): size-independent properties: exact symmetry, positive
+    semi-definiteness, information gain, rank = n - 7 gauge directions, every track accepted (the oracle's flags: fixture)."""
     wl = synth.make_window_workload(n_features=2000, n_clones=60, seq=30)
     g = make_engine(np.float64, max_clones=64, max_tracks=2048, max_obs=2048 * 60)
     synth.drive(g, wl, marginalize_last=False)
     P0 = g.getCovariance()
     g.marginalize()
     rep = g.lastReport()
-    assert rep["valid"].all() and rep["accepted"].sum() >= 1990
+    assert rep["valid"].all() and rep["accepted"].all()  # = the oracle's flags (tests/golden/stress_f64_2000x60_*.npz): zero flips
     P1 = g.getCovariance()
     n = P1.shape[0]
     assert n == 15 + 6 * 60 and np.isfinite(P1).all()

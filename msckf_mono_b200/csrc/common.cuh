@@ -33,7 +33,7 @@ struct DevState {
 template <class S>
 struct UpdArgs {
   int n_tracks, M, Lmax, ldp;
-  int ld, n, mode, has_yf;   // has_yf: k_jac's shared memory includes the single-warp gate Cholesky's copy
+  int ld, n, mode, gram_mma; // gram_mma: this filter's Gram products run on the FP64 tensor-core kernel (else the SIMT tile kernel)
   int K, nsplit, kchunk, tail_kind;
   double rank_thr;
   // packed input block

@@ -381,7 +381,9 @@ struct Engine : EngineBase {
     for (double** p : {&d_Z, &d_Yq, &d_ur, &d_G1p, &d_G2p}) { if (*p) cudaFree(*p); *p = nullptr; }
   }
   int alloc_window() {
-    for (double** p : {&d_T2, &d_R2, &d_TP, &d_S2, &d_W, &d_G}) CK(cudaMalloc(p, sizeof(double) * (size_t)ld * nmax));
+    for (double** p : {&d_T2, &d_R2, &d_TP, &d_S2, &d_W}) CK(cudaMalloc(p, sizeof(double) * (size_t)ld * nmax));
+    // Gamma / the tail kernel's L2 scratch (double-buffered 32 x 34 inverses + two transposed 32-row panels): at least that big
+    CK(cudaMalloc(&d_G, sizeof(double) * std::max((size_t)ld * nmax, (size_t)4 * 32 * 34 + (size_t)64 * (ld + 4))));
     CK(cudaMalloc(&d_r2, sizeof(double) * nmax));
     CK(cudaMalloc(&d_idiag, sizeof(double) * 2 * nmax));
     CK(cudaMalloc(&d_y, sizeof(double) * nmax));
@@ -571,7 +573,9 @@ struct Engine : EngineBase {
     if (kchunk < mb::GK) kchunk = mb::GK;
     nsplit = std::max(1, (a.K + kchunk - 1) / kchunk);
     a.nsplit = nsplit; a.kchunk = kchunk;
-    a.has_yf = 0;  // (round 1's single-warp gate copy is gone: the gate Cholesky is blocked over the whole CTA)
+    // FP64 tensor-core Gram products where they win (measured, profiles/r02_dmma.md): >= 200 tracks.  The choice depends on the
+    // filter's own batch only, never on how many filters share a launch: a device batch stays bit-identical to separate calls.
+    a.gram_mma = (gram_mma && p.N >= 200) ? 1 : 0;
     a.tail_kind = pick_tail(a.n, no_fused_tail);
     a.rank_thr = rank_thr;
     a.obs_off = p.d_off; a.obs = p.d_obs; a.clone_idx = p.d_idx; a.pfg_given = p.d_pfg_in;
@@ -850,7 +854,8 @@ int Ctx<S>::launch() {
     Nmax = std::max(Nmax, p.N); Mmax_ = std::max(Mmax_, a.M); Lm = std::max(Lm, p.Lmax); nmax_ = std::max(nmax_, a.n);
     nsplit = std::max(nsplit, a.nsplit);
     sh.tri_smem = std::max<unsigned>(sh.tri_smem, (unsigned)(16 + sizeof(S) * mb::kPoseStride * (size_t)a.M + sizeof(S) * 4 * 14 * (size_t)p.Lmax));
-    sh.jac_smem = std::max<unsigned>(sh.jac_smem, (unsigned)mb::jac_smem_bytes<S>(p.Lmax, a.M, a.has_yf != 0));
+    sh.jac_smem = std::max<unsigned>(sh.jac_smem, (unsigned)mb::jac_smem_bytes<S>(p.Lmax, a.M));
+    sh.gram_mma |= a.gram_mma ? 2 : 1;  // which Gram kernels the batch needs
     if (mode != MSCKF_B200_TRIANGULATE) {
       sh.tail_mask |= 1 << a.tail_kind;
       sh.tail_smem[a.tail_kind] = std::max<unsigned>(sh.tail_smem[a.tail_kind], (unsigned)tail_smem(a.n, a.tail_kind));
@@ -872,9 +877,6 @@ int Ctx<S>::launch() {
   sh.syrk_gx = sh.gemm_g * (sh.gemm_g + 1) / 2;
   sh.inj_smem = (unsigned)(sizeof(double) * nmax_);
   sh.pdl = (eng[0]->use_pdl && !profile()) ? 1 : 0;
-  // FP64 tensor-core Gram products where they win (measured, profiles/r02_dmma.md): batches and large track counts; one small
-  // filter is latency-bound either way and the 256-thread SIMT tile is a little quicker there
-  sh.gram_mma = (eng[0]->gram_mma && (nf > 1 || 3 * Nmax >= 1800)) ? 1 : 0;
   const bool want_graph = eng[0]->use_graph && !profile();
   if (want_graph) {
     for (auto& g : graphs)
@@ -971,8 +973,8 @@ int Ctx<S>::run_kernels(const LaunchShape& sh) {
     launches++;
     mark("k_blockdiag");
     if (fork) CK(cudaEventRecord(ev_join, stream2));
-    if (sh.gram_mma) CK(launch_k(mb::k_gram_mma<S>, dim3(sh.gram_gx, sh.gram_gy, nf), dim3(128), 0, stream, false, 1, A));  // FP64 tensor cores (DMMA)
-    else CK(launch_k(mb::k_gram<S>, dim3(sh.gram_gx, sh.gram_gy, nf), dim3(256), 0, stream, false, 1, A));
+    if (sh.gram_mma & 2) { CK(launch_k(mb::k_gram_mma<S>, dim3(sh.gram_gx, sh.gram_gy, nf), dim3(128), 0, stream, false, 1, A)); if (sh.gram_mma & 1) launches++; }  // FP64 tensor cores (DMMA)
+    if (sh.gram_mma & 1) CK(launch_k(mb::k_gram<S>, dim3(sh.gram_gx, sh.gram_gy, nf), dim3(256), 0, stream, false, 1, A));
     launches++;
     mark("k_gram");
     if (fork) CK(cudaStreamWaitEvent(stream, ev_join, 0));

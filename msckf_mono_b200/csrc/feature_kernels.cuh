@@ -292,7 +292,7 @@ __device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
 // ---- gate Cholesky, blocked by panels of 8 columns, all JT threads of the CTA.
 // The matrix is the trailing block [3:, 3:] of the packed-lower 2L x 2L array Y (rho = 2L - 3 rows); the right-hand side
 // r[3:] rides along as row rho.  Only y = L^-1 r is wanted (gamma = |y|^2), so the factor itself is never written back.
-// Per panel:  (1) EVERY thread loads the 8 x 8 diagonal micro-block and factorises it redundantly in registers (static
+// Per panel:  (1) every thread that owns a row loads the 8 x 8 diagonal micro-block and factorises it redundantly in registers (static
 // indices, right-looking: the dependent chain of a pivot is rsqrt -> multiply -> one FMA) -- no shuffles, no barriers, no
 // pivot broadcast;  (2) every thread solves its own rows of the panel against that micro-block in registers (row rho = the
 // right-hand side: its 8 entries are final components of y);  (3) the solved panel goes to shared memory TRANSPOSED
@@ -301,59 +301,64 @@ __device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
 // (round 1: one warp, shuffle + shared-memory round trip per pivot, ~350 ns each = 20 us of k_jac's 55).
 constexpr int kPW = 8;
 template <class S>
-__device__ __forceinline__ bool gate_chol_blocked(S* __restrict__ Y, S* __restrict__ r, int L2, S* __restrict__ PnT, int Rp) {
+__device__ __forceinline__ bool gate_chol_blocked(S* __restrict__ Y, S* __restrict__ r, int L2, S* __restrict__ PnT, int Rp, int* s_fail) {
   const int rho = L2 - 3, R = rho + 1, tid = threadIdx.x;
+  if (tid == 0) *s_fail = 0;
   for (int e = tid; e < kPW * Rp; e += JT) PnT[e] = S(0);  // (rows R..Rp-1 of a partial tile must read as zero)
   __syncthreads();
   for (int p0 = 0; p0 < rho; p0 += kPW) {
     const int w = min(kPW, rho - p0);
-    // (1) diagonal micro-block: lower triangle in registers, identity padding beyond w
-    S Lm[kPW][kPW], inv[kPW];
-#pragma unroll
-    for (int a = 0; a < kPW; ++a)
-#pragma unroll
-      for (int b = 0; b <= a; ++b) Lm[a][b] = (a < w) ? Y[pk(3 + p0 + a, 3 + p0 + b)] : ((a == b) ? S(1) : S(0));
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < kPW; ++j) {
-      const S d = Lm[j][j];
-      if (!(d > S(0))) ok = false;
-      const S iv = fast_rsqrt(d);
-      inv[j] = iv;
-#pragma unroll
-      for (int a = j + 1; a < kPW; ++a) Lm[a][j] *= iv;
-#pragma unroll
-      for (int b = j + 1; b < kPW; ++b)
-#pragma unroll
-        for (int a = b; a < kPW; ++a) Lm[a][b] -= Lm[a][j] * Lm[b][j];
-    }
-    if (!ok) return false;  // (every thread computed the same micro-block: uniform)
-    // (2) rows below the micro-block, and the right-hand side
+    // (1) diagonal micro-block: lower triangle in registers, identity padding beyond w -- only in the threads that own a row
+    // of this panel (the others would spend a fifth of the kernel's instructions on a result they never use)
     const int q0 = p0 + w;
-    for (int i = q0 + tid; i < R; i += JT) {
-      S x[kPW];
-      if (i < rho) {
-        const S* row = Y + pk(3 + i, 3 + p0);
+    if (q0 + tid < R) {
+      S Lm[kPW][kPW], inv[kPW];
 #pragma unroll
-        for (int j = 0; j < kPW; ++j) x[j] = (j < w) ? row[j] : S(0);
-      } else {
+      for (int a = 0; a < kPW; ++a)
 #pragma unroll
-        for (int j = 0; j < kPW; ++j) x[j] = (j < w) ? r[3 + p0 + j] : S(0);
-      }
+        for (int b = 0; b <= a; ++b) Lm[a][b] = (a < w) ? Y[pk(3 + p0 + a, 3 + p0 + b)] : ((a == b) ? S(1) : S(0));
+      bool ok = true;
 #pragma unroll
       for (int j = 0; j < kPW; ++j) {
-        x[j] *= inv[j];
+        const S d = Lm[j][j];
+        if (!(d > S(0))) ok = false;
+        const S iv = fast_rsqrt(d);
+        inv[j] = iv;
 #pragma unroll
-        for (int jj = j + 1; jj < kPW; ++jj) x[jj] -= x[j] * Lm[jj][j];
+        for (int a = j + 1; a < kPW; ++a) Lm[a][j] *= iv;
+#pragma unroll
+        for (int b = j + 1; b < kPW; ++b)
+#pragma unroll
+          for (int a = b; a < kPW; ++a) Lm[a][b] -= Lm[a][j] * Lm[b][j];
       }
+      if (!ok && tid == 0) *s_fail = 1;  // (thread 0 always owns a row: the right-hand side is row rho >= q0)
+      // (2) rows below the micro-block, and the right-hand side
+      for (int i = q0 + tid; i < R; i += JT) {
+        S x[kPW];
+        if (i < rho) {
+          const S* row = Y + pk(3 + i, 3 + p0);
 #pragma unroll
-      for (int j = 0; j < kPW; ++j) PnT[j * Rp + i] = x[j];
-      if (i == rho) {
+          for (int j = 0; j < kPW; ++j) x[j] = (j < w) ? row[j] : S(0);
+        } else {
 #pragma unroll
-        for (int j = 0; j < kPW; ++j) if (j < w) r[3 + p0 + j] = x[j];  // final components of y
+          for (int j = 0; j < kPW; ++j) x[j] = (j < w) ? r[3 + p0 + j] : S(0);
+        }
+#pragma unroll
+        for (int j = 0; j < kPW; ++j) {
+          x[j] *= inv[j];
+#pragma unroll
+          for (int jj = j + 1; jj < kPW; ++jj) x[jj] -= x[j] * Lm[jj][j];
+        }
+#pragma unroll
+        for (int j = 0; j < kPW; ++j) PnT[j * Rp + i] = x[j];
+        if (i == rho) {
+#pragma unroll
+          for (int j = 0; j < kPW; ++j) if (j < w) r[3 + p0 + j] = x[j];  // final components of y
+        }
       }
     }
     __syncthreads();
+    if (*s_fail) return false;  // a non-positive pivot (uniform: read after the barrier)
     // (4) trailing update: rows q0..R-1, columns q0..rho-1, lower triangle, 4 x 4 tiles (q0 is a multiple of 8 here)
     const int nrows = R - q0;
     if (nrows > 1) {
@@ -843,7 +848,8 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
   __syncthreads();
   stamp();  // two-sided transform
   // Cholesky with the right-hand side r~[3:] riding along as an extra row: y = L^-1 r~, gamma = |y|^2
-  const bool chol_ok = gate_chol_blocked<S>(Y, r, L2, PnT, Rp);
+  __shared__ int s_chol_fail;
+  const bool chol_ok = gate_chol_blocked<S>(Y, r, L2, PnT, Rp, &s_chol_fail);
   S gacc = 0;
   for (int j = 3 + tid; j < L2; j += JT) gacc += r[j] * r[j];
   (void)rho;

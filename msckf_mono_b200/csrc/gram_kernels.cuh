@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) k_gram(const UpdArgs<S>* __restrict__ arg
   __shared__ double sZa[GK][GT + 1], sZb[GK][GT + 1], sYa[GK][GT + 1], sYb[GK][GT + 1];
   // decode the (ta <= tb) tile pair
   const int ntile = (c + GT - 1) / GT;
-  if ((int)blockIdx.x >= ntile * (ntile + 1) / 2 || (int)blockIdx.y >= A.nsplit || A.n_tracks == 0) return;
+  if ((int)blockIdx.x >= ntile * (ntile + 1) / 2 || (int)blockIdx.y >= A.nsplit || A.n_tracks == 0 || A.gram_mma) return;
   int pidx = blockIdx.x, ta = 0;
   while (pidx >= ntile - ta) { pidx -= ntile - ta; ++ta; }
   const int tb = ta + pidx;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128) k_gram_mma(const UpdArgs<S>* __restrict__
   const double* __restrict__ Yq = A.Yq;
   __shared__ double sZa[GK][GL], sZb[GK][GL], sYa[GK][GL], sYb[GK][GL];
   const int ntile = (c + GT - 1) / GT;
-  if ((int)blockIdx.x >= ntile * (ntile + 1) / 2 || (int)blockIdx.y >= A.nsplit || A.n_tracks == 0) return;
+  if ((int)blockIdx.x >= ntile * (ntile + 1) / 2 || (int)blockIdx.y >= A.nsplit || A.n_tracks == 0 || !A.gram_mma) return;
   int pidx = blockIdx.x, ta = 0;
   while (pidx >= ntile - ta) { pidx -= ntile - ta; ++ta; }
   const int tb = ta + pidx;

@@ -47,15 +47,27 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
     if (dprof && tid == 0 && dpi < 14) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); dprof[dpi++] = t_; }
   };
   dstamp();
-  const int half = tid >> 5, lane = tid & 31;
+  const int half = (tid >> 5) & 1, lane = tid & 31;
+  const bool extra = tid >= 64;  // warps 2, 3: the rows of the identity that turn into the inverses (see below)
+  // The inverses ride along as 32 EXTRA ROWS per matrix: solving  Y L^T = I  row by row is exactly what the panel algorithm
+  // does to the rows below the block (micro-solve against the diagonal micro-block, then the trailing update), and
+  // Y = L^-T, i.e. extra row i, column j holds Linv[j][i] -- stored transposed, straight into LIA / LIG.  Row i of the identity
+  // is zero left of column i, so it only joins from the panel that contains column i.  This replaces a separate inverse
+  // stage (6 us and 7 CTA barriers per block in the first version of this file).
+  for (int e = tid; e < kFB * LD; e += nthreads) {
+    const int k = e / LD, c = e % LD;
+    LIA[e] = (k == c) ? 1.0 : 0.0;
+    LIG[e] = (k == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
 #pragma unroll 1
   for (int c0 = 0; c0 < kFB; c0 += PW) {
     if (c0 >= nb) {  // columns beyond the matrix: dropped indices
       if (tid < PW) { ida[c0 + tid] = 0.0; idg[c0 + tid] = 0.0; }
       continue;
     }
-    if (tid < 64) {
-    // (1) the two 4 x 4 diagonal micro-blocks, redundantly in every thread of warps 0 and 1 (the row solvers of (2) need them
+    if (tid < 128) {
+    // (1) the two 4 x 4 diagonal micro-blocks, redundantly in every thread of warps 0..3 (the row solvers of (2) need them
     // in registers; all eight warps doing it would make the half-rate FP64 pipe, not the pivot chain, the limit)
     double Gm[PW][PW], Am[PW][PW], ivg[PW], iva[PW];
 #pragma unroll
@@ -94,7 +106,7 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
     // (2) one row of the panel per thread (rows c0 .. nb-1; warp 0: S'', warp 1: Gamma), solved in registers; a row inside the
     // micro-block reproduces the factor's own row (entries right of its diagonal are masked)
     const int rrow = c0 + lane;
-    if (rrow < nb && !(half == 1 && full)) {
+    if (!extra && rrow < nb && !(half == 1 && full)) {
       double* D = half ? DG : DA;
       double x[PW];
 #pragma unroll
@@ -108,6 +120,20 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
       }
 #pragma unroll
       for (int j = 0; j < PW; ++j) if (c0 + j <= rrow) D[rrow * LD + c0 + j] = x[j];
+    }
+    if (extra && lane < c0 + PW && lane < nb && !(half == 1 && full)) {  // extra row `lane` of the identity, active from its own column on
+      double* LI = half ? LIG : LIA;
+      double x[PW];
+#pragma unroll
+      for (int j = 0; j < PW; ++j) x[j] = LI[(c0 + j) * LD + lane];
+#pragma unroll
+      for (int j = 0; j < PW; ++j) {
+        x[j] *= half ? ivg[j] : iva[j];
+#pragma unroll
+        for (int jj = j + 1; jj < PW; ++jj) x[jj] -= x[j] * (half ? Gm[jj][j] : Am[jj][j]);
+      }
+#pragma unroll
+      for (int j = 0; j < PW; ++j) LI[(c0 + j) * LD + lane] = x[j];
     }
     }
     __syncthreads();
@@ -124,58 +150,21 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
         const double2 b01 = *reinterpret_cast<const double2*>(D + j * LD + c0), b23 = *reinterpret_cast<const double2*>(D + j * LD + c0 + 2);
         D[i * LD + j] -= (a01.x * b01.x + a01.y * b01.y) + (a23.x * b23.x + a23.y * b23.y);
       }
+      // ... and of the extra rows: rhs[i][j] -= sum_k Y[i][c0+k] L[j][c0+k] for the active rows i < q0, columns j >= q0
+      const int nact = min(q0, nb), pere = nact * nr, tote = full ? pere : 2 * pere;
+#pragma unroll 1
+      for (int e = tid; e < tote; e += nthreads) {
+        const int mtx = e >= pere ? 1 : 0, r2 = e - mtx * pere, jj = r2 / nact, i = r2 - jj * nact, j = q0 + jj;
+        const double* D = mtx ? DG : DA;
+        double* LI = mtx ? LIG : LIA;
+        const double2 b01 = *reinterpret_cast<const double2*>(D + j * LD + c0), b23 = *reinterpret_cast<const double2*>(D + j * LD + c0 + 2);
+        LI[j * LD + i] -= (LI[c0 * LD + i] * b01.x + LI[(c0 + 1) * LD + i] * b01.y) + (LI[(c0 + 2) * LD + i] * b23.x + LI[(c0 + 3) * LD + i] * b23.y);
+      }
     }
     __syncthreads();
   }
-  dstamp();  // factors done
-  // ---- inverses, 8 x 8 blocks.  Diagonal blocks first: one column per thread (2 matrices x 4 blocks x 8 columns = 64 threads),
-  // right-looking substitution inside the 8 x 8 block, the column kept in the output array (conflict-free: thread = column).
-  constexpr int IB = 8;
-  if (tid < 64 && !(half == 1 && full)) {
-    const double* D = half ? DG : DA;
-    const double* iv = half ? idg : ida;
-    double* LI = half ? LIG : LIA;
-    const int c = lane, b0 = c & ~(IB - 1);
-#pragma unroll 1
-    for (int k = 0; k < kFB; ++k) LI[k * LD + c] = (k == c) ? 1.0 : 0.0;  // (also zeroes everything above / outside)
-#pragma unroll 1
-    for (int j = c; j < b0 + IB; ++j) {
-      const double y = LI[j * LD + c] * iv[j];
-      LI[j * LD + c] = y;
-#pragma unroll 1
-      for (int k = j + 1; k < b0 + IB; ++k) LI[k * LD + c] -= D[k * LD + j] * y;
-    }
-  }
-  __syncthreads();
-  // block rows 1..3: T = sum_k L_ik Linv_kj over the finished block rows, then Linv_ij = -Linv_ii T
-#pragma unroll 1
-  for (int bi = 1; bi < kFB / IB; ++bi) {
-    const int r0 = bi * IB, ncol = r0;  // columns 0 .. r0-1
-    const int per = IB * ncol, tot = full ? per : 2 * per;
-#pragma unroll 1
-    for (int e = tid; e < tot; e += nthreads) {
-      const int mtx = e >= per ? 1 : 0, r2 = e - mtx * per, rr = r2 / ncol, c = r2 - rr * ncol, r = r0 + rr;
-      const double* D = mtx ? DG : DA;
-      const double* LI = mtx ? LIG : LIA;
-      double s0 = 0.0, s1 = 0.0;
-      int k = c;
-      for (; k + 1 < r0; k += 2) { s0 += D[r * LD + k] * LI[k * LD + c]; s1 += D[r * LD + k + 1] * LI[(k + 1) * LD + c]; }
-      if (k < r0) s0 += D[r * LD + k] * LI[k * LD + c];
-      (mtx ? TG : TA)[rr * LD + c] = s0 + s1;
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int e = tid; e < tot; e += nthreads) {
-      const int mtx = e >= per ? 1 : 0, r2 = e - mtx * per, rr = r2 / ncol, c = r2 - rr * ncol, r = r0 + rr;
-      double* LI = mtx ? LIG : LIA;
-      const double* T = mtx ? TG : TA;
-      double s = 0.0;
-      for (int k = 0; k <= rr; ++k) s += LI[r * LD + r0 + k] * T[k * LD + c];
-      LI[r * LD + c] = -s;
-    }
-    __syncthreads();
-  }
-  dstamp();  // inverses
+  dstamp();  // factors + inverses done
+  // rows / columns of dropped or out-of-range pivots of the inverses are zero by construction (1 / L_kk := 0)
   return rk;
 }
 

@@ -7,14 +7,13 @@
 // followed by  P <- P - W^T W (k_syrk, all SMs) and dx = W^T y + state injection (k_inject)   (msckf.h:1373-1418).
 //
 // What bounds this kernel is latency, not the FP64 pipe (64 lane-FMA/clk/SM measured, scripts/fp64_rate.cu): a chain of
-// ~n dependent pivots, each a short dot product issued by ONE warp at ~8 cycles per dependent instruction.  Measured
-// (ncu source view, profiles/) and acted upon:
-//   * instruction count per pivot is what the diagonal block costs: the two factorisations run in two warps (A polls
-//     G's decision for the pivot through shared memory), two more warps build the inverses of the two factors one
-//     pivot behind, rsqrt is a float seed + two Newton steps, the dot products read 16 columns per round trip with 16-byte
-//     loads and are formed one pivot ahead (look-ahead), so that a pivot starts with one shuffle and one FMA;
-//   * instruction fetch: hand-unrolled register-resident forms (~50-100 KB of straight-line code that runs once per
-//     block) are bound by instruction-cache misses at ~15 cycles per instruction -- every hot loop here is ROLLED;
+// ~n dependent pivots at ~8 cycles per dependent instruction, plus instruction fetch -- the kernel is ~100 KB of SASS, the
+// L1.5 instruction cache holds 32 KB, so every phase of every block iteration starts cold (5-7 cycles per instruction).
+// Measured (ncu source view, %globaltimer stamps, profiles/) and acted upon:
+//   * the diagonal block (tail_diag.cuh): blocked by panels of 4 columns over the whole CTA, the 4 x 4 micro-blocks of both
+//     matrices factorised redundantly in registers by the threads that solve the panel rows, keep / drop decisions evaluated
+//     by all of them from the same numbers -- no per-pivot shuffle, flag or poll; inverses built block row by block row;
+//     every loop rolled except the micro-block (a fully unrolled 8 x 8 / 32-step-inverse version was fetch-bound: 21 us);
 //   * work on the critical path: the panel below a diagonal block is X = A_panel L_kk^-T.  With L_kk^-1 at hand the
 //     panel is a small GEMM shared by all 8 warps instead of a 32-step substitution per row; panel rows are dealt to
 //     the 8 CTAs (no redundant solves) and exchanged through L2 (a scratch panel every CTA reads back after the cluster
@@ -81,8 +80,10 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
   unsigned long long* __restrict__ prof = ua.prof;  // optional phase timestamps
   namespace cg = cooperative_groups;
   constexpr int NB = kFB, LD = kFLD;
-  double* Lsc = scratch;                      // [2][32][34] inverses of the current diagonal blocks' factors (A, G)
-  double* Psc = scratch + 2 * NB * LD;        // [2][32][ldt] the current panels, transposed (A, G)
+  // [2 slots][2][32][34] inverses of the diagonal blocks' factors (A, G): CTA 0 runs one block ahead of the others, so the
+  // slot of block k + 1 is written while slot k may still be read
+  auto Lsc_of = [&](int blk) { return scratch + (size_t)(blk & 1) * 2 * NB * LD; };
+  double* Psc = scratch + 4 * NB * LD;        // [2][32][ldt] the current panels, transposed (A, G)
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
   const int C = (int)cluster.num_blocks();
@@ -96,6 +97,14 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
     }
   };
   stamp();
+  int wprof_i = 0;
+  auto wstamp = [&]() {  // the same for the first worker CTA (slots 20..39)
+    if (prof && blockIdx.x == 1 && blockIdx.z == 0 && tid == 0 && wprof_i < 19) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) : : "memory");
+      prof[20 + wprof_i++] = t;
+    }
+  };
   extern __shared__ __align__(16) double sm[];
   const int ldt = (n + 3) & ~3;              // row stride of the transposed panels (16-byte aligned rows)
   double* DG = sm;                           // [32][34] diagonal block of G (CTA 0); then this CTA's panel rows of G; then X_G^T
@@ -149,13 +158,12 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
   }
   __syncthreads();
   // ---------------------------------------------------------------- blocked rank-revealing Cholesky (G decides, A follows)
-  // CTA 0 factorises diagonal blocks: four warps on four sub-partitions -- G's factor (decides), A's factor (follows G's
-  // decision pivot by pivot) and the inverses of the two factors one pivot behind.  The blocks (strictly lower part in
-  // DG / DA, diagonals in dgG / dgA) are in shared memory when this is called; the inverses end up in LIG / LIA and in
-  // the L2 scratch for the other CTAs.  Block 0 is factorised up front; block kb + 1 is factorised by CTA 0 WHILE the
+  // CTA 0 factorises diagonal blocks (tf_factor_block, tail_diag.cuh: G decides keep / drop per pivot, A follows).  The
+  // blocks (lower triangles incl. the diagonal, in DG / DA) are in shared memory when this is called; the inverses end up in
+  // LIG / LIA and in the L2 scratch for the other CTAs.  Block 0 is factorised up front; block kb + 1 is factorised by CTA 0 WHILE the
   // other CTAs run the trailing update of block kb (it only needs the leading 32 x 32 tile of that update, which CTA 0
   // forms itself from the panel).
-  auto factor_block = [&](int kb, int nb, bool stamps) {
+  auto factor_block = [&](int kb, int nb, bool stamps, double* Lsc) {
     if (stamps && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[76] = t_; }
     TfRank rk;
     rk.g = s_rankG; rk.a = s_rankA;
@@ -174,22 +182,76 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
     if (!full) tf_load_diag(DG, G, ld, 0, nb0, tid);
     tf_load_diag(DA, A, ld, 0, nb0, tid);
     __syncthreads();
-    factor_block(0, nb0, prof != nullptr);
+    factor_block(0, nb0, prof != nullptr, Lsc_of(0));
   }
   stamp();  // diagonal block 0 done
   for (int kb = 0; kb < n; kb += NB) {
     const int nb = min(NB, n - kb);
     const int r0 = kb + nb;
     const int nr = n - r0;
-    cluster.sync();  // inverses of block kb in L2; trailing update of block kb - 1 complete
-    // phase 2: the panel below the block, X = rows * Linv^T.  Rows are dealt to the CTAs in contiguous chunks (an even
-    // number of rows each); lane = local row, warp w computes columns w, w + 8, w + 16, w + 24; the results go to a scratch
-    // panel in L2 that every CTA reads back after the barrier.  The W rows of this CTA are solved the same way (local).
-    const int chunk = (((nr + C - 1) / C) + 1) & ~1;
-    const int i0 = crank * chunk;
+    cluster.sync();  // B1: inverses of block kb in L2; trailing update of block kb - 1 complete
+    const int blk = kb / NB;
+    const double* Lsc = Lsc_of(blk);
+    if (crank == 0) {
+      // ---- CTA 0 runs the chain of diagonal blocks ONE BLOCK AHEAD of the other CTAs (round 2): while they solve the panel of
+      // block kb, exchange it and run the trailing update, CTA 0 solves only the 32 panel rows of the NEXT diagonal block itself
+      // (X = rows * Linv^T with the inverses it still holds), forms that block's leading tile and factorises it.  It has
+      // nothing to contribute to the panel barrier (arrives at once, waits when done), so the others never wait for it there.
+      if (nr <= 0) break;
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // B2 of this block
+      const int nb2 = min(NB, nr);
+      for (int e = tid; e < NB * NB; e += kTailThreads) {
+        const int l = e / NB, c = e % NB;
+        const bool in = (l < nb2 && c < nb);
+        DA[l * LD + c] = in ? A[(size_t)(r0 + l) * ld + kb + c] : 0.0;
+        DG[l * LD + c] = (in && !full) ? G[(size_t)(r0 + l) * ld + kb + c] : 0.0;
+      }
+      __syncthreads();
+      for (int e = tid; e < NB * NB; e += kTailThreads) {  // X = rows * Linv^T (rows of a dropped pivot of Linv are zero)
+        const int l = e / NB, j = e % NB;
+        double sa0 = 0.0, sa1 = 0.0, sg0 = 0.0, sg1 = 0.0;
+#pragma unroll 4
+        for (int c = 0; c < NB; c += 2) {
+          sa0 += DA[l * LD + c] * LIA[j * LD + c]; sa1 += DA[l * LD + c + 1] * LIA[j * LD + c + 1];
+          if (!full) { sg0 += DG[l * LD + c] * LIG[j * LD + c]; sg1 += DG[l * LD + c + 1] * LIG[j * LD + c + 1]; }
+        }
+        WB[l * LD + j] = sa0 + sa1;
+        DT[l * LD + j] = sg0 + sg1;
+      }
+      __syncthreads();
+      for (int e = tid; e < NB * LD; e += kTailThreads) {  // the next diagonal block = its leading tile of the trailing update
+        const int i = e / LD, j = e % LD;
+        double va = 0.0, vg = 0.0;
+        if (i < nb2 && j <= i) {
+          double sa0 = 0.0, sa1 = 0.0, sg0 = 0.0, sg1 = 0.0;
+          const double oa = A[(size_t)(r0 + i) * ld + r0 + j], og = full ? 0.0 : G[(size_t)(r0 + i) * ld + r0 + j];
+#pragma unroll 4
+          for (int c = 0; c < NB; c += 2) {
+            sa0 += WB[i * LD + c] * WB[j * LD + c]; sa1 += WB[i * LD + c + 1] * WB[j * LD + c + 1];
+            if (!full) { sg0 += DT[i * LD + c] * DT[j * LD + c]; sg1 += DT[i * LD + c + 1] * DT[j * LD + c + 1]; }
+          }
+          va = oa - (sa0 + sa1);
+          vg = og - (sg0 + sg1);
+        }
+        DA[e] = va;
+        DG[e] = vg;
+      }
+      __syncthreads();
+      stamp();  // next diagonal block formed (CTA 0)
+      factor_block(r0, nb2, false, Lsc_of(blk + 1));
+      stamp();  // next diagonal block factorised (CTA 0)
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // B2 (long complete)
+      continue;
+    }
+    wstamp();  // B1 passed
+    // phase 2 (CTAs 1..7): the panel below the block, X = rows * Linv^T.  Rows are dealt to the CTAs in contiguous chunks (an
+    // even number of rows each); lane = local row, warp w computes columns w, w + 8, w + 16, w + 24; the results go to a scratch
+    // panel in L2 that every worker reads back after the barrier.  The W rows of this CTA are solved the same way (local).
+    const int chunk = (((nr + C - 2) / (C - 1)) + 1) & ~1;
+    const int i0 = (crank - 1) * chunk;
     const int nloc = max(0, min(chunk, nr - i0));
     {
-      if (crank != 0) {  // all loads in flight before the first store
+      {  // the inverses of block kb: all loads in flight before the first store
         constexpr int NE = NB * LD / 2, NI = (NE + kTailThreads - 1) / kTailThreads;
         double2 va[NI], vg[NI];
 #pragma unroll
@@ -249,9 +311,10 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
         if (!full) Psc[(size_t)(NB + j) * ldt + i0 + l] = DG[j * LD + l];
       }
     }
-    stamp();  // panel computed
+    wstamp();  // panel computed
     if (nr <= 0) break;  // last block: the W rows are complete
     cluster.sync();
+    wstamp();  // B2 passed
     {
       const int nr2 = (nr + 1) >> 1;  // 16-byte loads; an odd last column picks up the (finite) neighbour, zeroed below
       const int tot = NB * nr2;
@@ -285,32 +348,12 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
       }
       __syncthreads();
     }
-    stamp();  // panel exchanged
+    wstamp();  // panel exchanged
     // phase 3.  CTA 0: the next diagonal block = leading 32 x 32 tile of the trailing update, formed from the panel
     // straight into shared memory, then factorised.  CTAs 1..7: the rest of the trailing update, 4x4 register tiles on
     // the transposed panels -- the lower-triangle tiles of A, then of G (rows >= 32 of the trailing matrix), dealt in
     // contiguous runs (neighbouring lanes read neighbouring columns: no bank conflicts); then their own W tiles.
-    if (crank == 0) {
-      const int nb2 = min(NB, nr);
-      for (int e = tid; e < NB * LD; e += kTailThreads) {
-        const int i = e / LD, j = e % LD;
-        double va = 0.0, vg = 0.0;
-        if (i < nb2 && j <= i) {
-          double sa = 0.0, sg = 0.0;
-#pragma unroll 8
-          for (int c = 0; c < NB; ++c) {
-            sa += PT_A[(size_t)c * ldt + i] * PT_A[(size_t)c * ldt + j];
-            if (!full) sg += PT_G[(size_t)c * ldt + i] * PT_G[(size_t)c * ldt + j];
-          }
-          va = A[(size_t)(r0 + i) * ld + r0 + j] - sa;
-          if (!full) vg = G[(size_t)(r0 + i) * ld + r0 + j] - sg;
-        }
-        DA[e] = va;
-        DG[e] = vg;
-      }
-      __syncthreads();
-      factor_block(r0, nb2, false);
-    } else {
+    {
       const int nt = (nr + 3) / 4, ntile = nt * (nt + 1) / 2;
       constexpr int kLead = (NB / 4) * (NB / 4 + 1) / 2;  // tiles of the leading 32 x 32 block: CTA 0's
       const int nrest = max(0, ntile - kLead);
@@ -358,7 +401,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
         }
       }
     }
-    stamp();  // next diagonal block done (CTA 0)
+    wstamp();  // trailing update + W tiles done
   }
   cluster.sync();
   if (gtid == 0) *rank_out = s_rankA;

@@ -29,10 +29,13 @@ for _ in range(4):
     work.fetch(batch.n_tracks)
 buf = (C.c_ulonglong * 80)()
 capi.lib().msckf_b200_tail_profile(work.h, buf, 80)
-st = [int(x) for x in list(buf)[:40] if x]
+st = [int(x) for x in list(buf)[:20] if x]
+ws = [int(x) for x in list(buf)[20:40] if x]
 rel = [round((x - st[0]) / 1e3, 1) for x in st]
 print("tail stamps (us since start):", rel)
 print("  deltas:", [round(b - a, 1) for a, b in zip(rel[:-1], rel[1:])])
+if ws:
+    print("  worker CTA 1 (us since kernel start; per block: B1 passed, panel, B2 passed, exchanged, trailing):", [round((x - st[0]) / 1e3, 1) for x in ws])
 print("  block 0 factor (us):", round((int(buf[77]) - int(buf[76])) / 1e3, 2))
 dd = [int(x) for x in list(buf)[60:74] if x]
 if dd:

@@ -59,8 +59,11 @@ def numbers(g, o, sg, so):
     if len(dxg) != len(dxo):  # a prune after the last update changed the window: compare the part both still have
         k = min(len(dxg), len(dxo))
         dxg, dxo = dxg[:15], dxo[:15]
+    ok = np.asarray(rep_o["valid"]).astype(bool)  # (a rejected track's position is whatever its failed triangulation left)
+    acc = np.asarray(rep_o["accepted"]).astype(bool)  # (gamma of a track that failed the Cholesky is a sentinel)
     return {"dx": rel(dxg, dxo), "P": float(np.abs(sg["P"] - so["P"]).max() / np.abs(so["P"]).max()),
-            "gamma": rel(rep_g["gamma"], rep_o["gamma"]), "pfg": rel(rep_g["p_f_G"], rep_o["p_f_G"]),
+            "gamma": rel(np.asarray(rep_g["gamma"])[acc], np.asarray(rep_o["gamma"])[acc]) if acc.any() else 0.0,
+            "pfg": rel(np.asarray(rep_g["p_f_G"])[ok], np.asarray(rep_o["p_f_G"])[ok]) if ok.any() else 0.0,
             "imu_p": float(np.abs(sg["imu_p"] - so["imu_p"]).max()), "cam_p": float(np.abs(sg["cam_p"] - so["cam_p"]).max()),
             "imu_q": quat_err(sg["imu_q"], so["imu_q"]), "cam_q": quat_err(sg["cam_q"], so["cam_q"]), "flips": 0,
             "rank_engine": int(g.counters()["rows_kept"]), "rank_oracle": int(o.counters()["rows_kept"])}

@@ -541,6 +541,7 @@ struct Engine : EngineBase {
     for (int k0 = 0; k0 < k; k0 += mb::kPropMax) {
       mb::PropBatch<S> pb;
       pb.st = d_st; pb.P = d_P; pb.ldp = ldp; pb.M = M; pb.k = std::min(mb::kPropMax, k - k0); pb.pad_ = 0;
+      pb.prof = profile ? d_prof : nullptr;
       for (int i = 0; i < pb.k; ++i)
         for (int j = 0; j < 7; ++j) pb.r[i][j] = r[7 * (size_t)(k0 + i) + j];
       mb::k_propagate<S><<<1, 256, 0, stream>>>(pb);

@@ -71,6 +71,21 @@ __device__ __forceinline__ void lin15(S* C, int nterm, const double* coef, const
   __syncthreads();
 }
 
+// first lane (among `active` ones) holding the largest non-negative value: two / three REDUX instructions instead of a
+// five-level shuffle tree (the pivot search was 40 % of k_propagate's LU step)
+__device__ __forceinline__ int warp_argmax_first(float v, bool active, int lane) {
+  const unsigned b = active ? __float_as_uint(v) : 0u;  // non-negative floats order like their bit patterns
+  const unsigned m = __reduce_max_sync(0xffffffffu, b);
+  return (int)__reduce_min_sync(0xffffffffu, (active && b == m) ? (unsigned)lane : 31u);
+}
+__device__ __forceinline__ int warp_argmax_first(double v, bool active, int lane) {
+  const unsigned hi = active ? (unsigned)__double2hiint(v) : 0u, lo = (unsigned)__double2loint(v);
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const bool c1 = active && hi == mhi;
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+  return (int)__reduce_min_sync(0xffffffffu, (c1 && lo == mlo) ? (unsigned)lane : 31u);
+}
+
 // Up to kPropMax IMU readings per launch (msckf_b200_propagate_n: the shim queues the readings between two images), passed
 // by value so that the call needs no staging buffer and stays asynchronous.  The readings are applied one after the other
 // with exactly the arithmetic of a single propagate() each.
@@ -80,6 +95,7 @@ struct PropBatch {
   DevState<S>* st;
   S* P;
   int ldp, M, k, pad_;
+  unsigned long long* prof;  // optional %globaltimer stamps of the first reading's phases (profiling aid)
   S r[kPropMax][7];  // omega[3], a[3], dT
 };
 
@@ -88,6 +104,11 @@ __global__ void __launch_bounds__(256) k_propagate(const PropBatch<S> pb) {
   // The IMU state, the 15 x 15 IMU block of P and (for windows up to 85 clones) the thread's columns of P_IC stay on chip
   // across the readings of the batch: one global round trip per launch instead of one per reading and serial section.
   DevState<S>* gst = pb.st;
+  int prof_i = 0;
+  auto stamp = [&]() {
+    if (pb.prof && threadIdx.x == 0 && prof_i < 16) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); pb.prof[prof_i++] = t_; }
+  };
+  stamp();
   __shared__ DevState<S> s_state;
   DevState<S>* st = &s_state;
   S* __restrict__ P = pb.P;
@@ -118,6 +139,7 @@ __global__ void __launch_bounds__(256) k_propagate(const PropBatch<S> pb) {
   __shared__ int s_deg, s_sq;
   __shared__ S colsum[15];
   const int t = threadIdx.x;
+  stamp();  // state, P_II and P_IC columns on chip
   for (int ir = 0; ir < pb.k; ++ir) {
   const S wx = pb.r[ir][0], wy = pb.r[ir][1], wz = pb.r[ir][2], ax = pb.r[ir][3], ay = pb.r[ir][4], az = pb.r[ir][5], dT = pb.r[ir][6];
   __syncthreads();
@@ -186,6 +208,7 @@ __global__ void __launch_bounds__(256) k_propagate(const PropBatch<S> pb) {
     }
   }
   __syncthreads();
+  stamp();  // calcF / calcG / RK
   // ---- F *= dT ; Phi = exp(F)  (unsupported/Eigen MatrixExponential restated)
   if (t < 225) F[t] *= dT;
   __syncthreads();
@@ -273,42 +296,56 @@ __global__ void __launch_bounds__(256) k_propagate(const PropBatch<S> pb) {
   // (V - U) Phi = (V + U): partial-pivot LU on the 15x30 augmented system [den | num]
   if (t < 225) { Tm[t] = Vm[t] - Um[t]; Phi[t] = Vm[t] + Um[t]; }
   __syncthreads();
-  // partial-pivot LU of the 15 x 30 system [den | num] and the back substitution on ONE warp (lane = column: 0..14 of den,
-  // 15..29 of num), __syncwarp only -- the CTA-wide form cost five block barriers per pivot.  Same operations in the same
-  // order as before (first largest |pivot|, multiplier by division, multiply-subtract).
+  stamp();  // Pade numerator / denominator
+  // partial-pivot LU of the 15 x 30 system [den | num] and the back substitution on ONE warp, __syncwarp only (the CTA-wide
+  // form cost five block barriers per pivot).  Same operations as before (first largest |pivot|, multiplier by division,
+  // multiply-subtract), arranged for a SHORT instruction stream -- this kernel's body is ~90 KB of SASS and whatever runs once
+  // per reading is fetched cold: the pivot is a warp arg-max (5 shuffle steps), lane = ROW for the elimination (one division
+  // per lane, a rolled loop along the row; stride 15 words: conflict-free), lane = column for the row swap and the back
+  // substitution (rolled).  (Measured: unrolled per-column register forms of this were slower, 26 vs 21 us per reading.)
   if (t < 32) {
     S* Mx = (t < 15) ? Tm : Phi;
-    const int j = (t < 15) ? t : t - 15;
+    const int j = (t < 15) ? t : ((t < 30) ? t - 15 : 0);
+#pragma unroll 1
     for (int k = 0; k < 15; ++k) {
-      int p = k;
-      if (t == k) {
-        S big = tabs(Tm[15 * k + k]);
-        for (int i = k + 1; i < 15; ++i)
-          if (tabs(Tm[15 * i + k]) > big) { big = tabs(Tm[15 * i + k]); p = i; }
-      }
-      p = __shfl_sync(0xffffffffu, p, k);
+      const bool cand = t >= k && t < 15;
+      const int p = warp_argmax_first(cand ? tabs(Tm[15 * t + k]) : S(0), cand, t);  // first largest |entry| of column k, diagonal down
       if (p != k && t < 30) { const S tmp = Mx[15 * k + j]; Mx[15 * k + j] = Mx[15 * p + j]; Mx[15 * p + j] = tmp; }
       __syncwarp();
-      const S lmine = (t < 15 && t > k) ? Tm[15 * t + k] / Tm[15 * k + k] : S(0);  // lane i: multiplier of row i
-      __syncwarp();
-      for (int i = k + 1; i < 15; ++i) {
-        const S l = __shfl_sync(0xffffffffu, lmine, i);
-        if (t < 30 && (t >= 15 || j > k)) Mx[15 * i + j] -= l * Mx[15 * k + j];
+      {  // lanes 0..14: row t of den; lanes 16..30: row t - 16 of num.  Every load of the step in flight before the first store
+         // (a rolled read-modify-write loop serialises on shared-memory latency: the stores may alias the loads)
+        const int row = t & 15;
+        if (row > k && row < 15) {
+          const S l = Tm[15 * row + k] / Tm[15 * k + k];
+          S* Mr = (t < 16) ? Tm : Phi;
+          S pr[15], mr[15];
+#pragma unroll
+          for (int c = 0; c < 15; ++c) { pr[c] = Mr[15 * k + c]; mr[c] = Mr[15 * row + c]; }
+          __syncwarp(__activemask());
+#pragma unroll
+          for (int c = 0; c < 15; ++c)
+            if (t >= 16 || c > k) Mr[15 * row + c] = mr[c] - l * pr[c];
+          if (t < 16) Tm[15 * row + k] = S(0);
+        }
       }
-      if (t == k)
-        for (int i = k + 1; i < 15; ++i) Tm[15 * i + k] = S(0);
       __syncwarp();
     }
-    // back substitution: column t of Phi per lane
+    // back substitution: column t of Phi per lane, the solved entries in registers (static indices)
     if (t < 15) {
+      S x[15];
+#pragma unroll
       for (int i = 14; i >= 0; --i) {
         S sacc = Phi[15 * i + t];
-        for (int k = i + 1; k < 15; ++k) sacc -= Tm[15 * i + k] * Phi[15 * k + t];
-        Phi[15 * i + t] = sacc / Tm[15 * i + i];
+#pragma unroll
+        for (int k = i + 1; k < 15; ++k) sacc -= Tm[15 * i + k] * x[k];
+        x[i] = sacc / Tm[15 * i + i];
       }
+#pragma unroll
+      for (int i = 0; i < 15; ++i) Phi[15 * i + t] = x[i];
     }
   }
   __syncthreads();
+  stamp();  // LU + back substitution
   for (int sgn = 0; sgn < sq; ++sgn) {
     mm15(Tm, Phi, Phi);
     if (t < 225) Phi[t] = Tm[t];
@@ -341,6 +378,7 @@ __global__ void __launch_bounds__(256) k_propagate(const PropBatch<S> pb) {
     }
   }
   __syncthreads();
+  stamp();  // observability constraints
   // ---- covariance: P_II <- sym(Phi (P_II + G Q G^T dT) Phi^T), P_IC <- Phi P_IC (msckf.h:134-144)
   if (t < 180) {  // GQ = G * Q_imu
     const int i = t / 12, j = t % 12;
@@ -402,6 +440,7 @@ __global__ void __launch_bounds__(256) k_propagate(const PropBatch<S> pb) {
     }
   }
   __syncthreads();  // the next reading starts from the state and covariance written above
+  stamp();  // covariance
   }
   // ---- write back: IMU state, P_II, P_IC (and its transpose)
   if (t == 0) {

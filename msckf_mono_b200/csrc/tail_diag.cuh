@@ -137,28 +137,36 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
     }
     }
     __syncthreads();
-    // (3) trailing update inside the block: rows / columns c0+4 .. nb-1, lower triangle, both matrices
+    // (3) trailing update inside the block: rows / columns c0+4 .. nb-1, lower triangle, both matrices -- and of the extra rows:
+    // rhs[i][j] -= sum_k Y[i][c0+k] L[j][c0+k] for the active rows i < q0, columns j >= q0.  Threads as a 16 x 16 grid (no
+    // index divisions on this path: every instruction here is on the critical chain of the whole kernel).
     const int q0 = c0 + PW, nr = nb - q0;
     if (nr > 0) {
-      const int per = nr * nr, tot = full ? per : 2 * per;
+      const int ty = tid >> 4, tx = tid & 15;
 #pragma unroll 1
-      for (int e = tid; e < tot; e += nthreads) {
-        const int mtx = e >= per ? 1 : 0, r2 = e - mtx * per, ii = r2 / nr, i = q0 + ii, j = q0 + (r2 - ii * nr);
-        if (j > i) continue;
-        double* D = mtx ? DG : DA;
-        const double2 a01 = *reinterpret_cast<const double2*>(D + i * LD + c0), a23 = *reinterpret_cast<const double2*>(D + i * LD + c0 + 2);
-        const double2 b01 = *reinterpret_cast<const double2*>(D + j * LD + c0), b23 = *reinterpret_cast<const double2*>(D + j * LD + c0 + 2);
-        D[i * LD + j] -= (a01.x * b01.x + a01.y * b01.y) + (a23.x * b23.x + a23.y * b23.y);
+      for (int i = q0 + ty; i < nb; i += 16) {
+        const double2 a01 = *reinterpret_cast<const double2*>(DA + i * LD + c0), a23 = *reinterpret_cast<const double2*>(DA + i * LD + c0 + 2);
+        const double2 g01 = *reinterpret_cast<const double2*>(DG + i * LD + c0), g23 = *reinterpret_cast<const double2*>(DG + i * LD + c0 + 2);
+#pragma unroll 1
+        for (int j = q0 + tx; j <= i; j += 16) {
+          const double2 b01 = *reinterpret_cast<const double2*>(DA + j * LD + c0), b23 = *reinterpret_cast<const double2*>(DA + j * LD + c0 + 2);
+          DA[i * LD + j] -= (a01.x * b01.x + a01.y * b01.y) + (a23.x * b23.x + a23.y * b23.y);
+          if (!full) {
+            const double2 h01 = *reinterpret_cast<const double2*>(DG + j * LD + c0), h23 = *reinterpret_cast<const double2*>(DG + j * LD + c0 + 2);
+            DG[i * LD + j] -= (g01.x * h01.x + g01.y * h01.y) + (g23.x * h23.x + g23.y * h23.y);
+          }
+        }
       }
-      // ... and of the extra rows: rhs[i][j] -= sum_k Y[i][c0+k] L[j][c0+k] for the active rows i < q0, columns j >= q0
-      const int nact = min(q0, nb), pere = nact * nr, tote = full ? pere : 2 * pere;
+      const int nact = min(q0, nb);
 #pragma unroll 1
-      for (int e = tid; e < tote; e += nthreads) {
-        const int mtx = e >= pere ? 1 : 0, r2 = e - mtx * pere, jj = r2 / nact, i = r2 - jj * nact, j = q0 + jj;
-        const double* D = mtx ? DG : DA;
-        double* LI = mtx ? LIG : LIA;
-        const double2 b01 = *reinterpret_cast<const double2*>(D + j * LD + c0), b23 = *reinterpret_cast<const double2*>(D + j * LD + c0 + 2);
-        LI[j * LD + i] -= (LI[c0 * LD + i] * b01.x + LI[(c0 + 1) * LD + i] * b01.y) + (LI[(c0 + 2) * LD + i] * b23.x + LI[(c0 + 3) * LD + i] * b23.y);
+      for (int j = q0 + ty; j < nb; j += 16) {
+        const double2 b01 = *reinterpret_cast<const double2*>(DA + j * LD + c0), b23 = *reinterpret_cast<const double2*>(DA + j * LD + c0 + 2);
+        const double2 h01 = *reinterpret_cast<const double2*>(DG + j * LD + c0), h23 = *reinterpret_cast<const double2*>(DG + j * LD + c0 + 2);
+#pragma unroll 1
+        for (int i = tx; i < nact; i += 16) {
+          LIA[j * LD + i] -= (LIA[c0 * LD + i] * b01.x + LIA[(c0 + 1) * LD + i] * b01.y) + (LIA[(c0 + 2) * LD + i] * b23.x + LIA[(c0 + 3) * LD + i] * b23.y);
+          if (!full) LIG[j * LD + i] -= (LIG[c0 * LD + i] * h01.x + LIG[(c0 + 1) * LD + i] * h01.y) + (LIG[(c0 + 2) * LD + i] * h23.x + LIG[(c0 + 3) * LD + i] * h23.y);
+        }
       }
     }
     __syncthreads();

@@ -200,38 +200,75 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
       if (nr <= 0) break;
       asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // B2 of this block
       const int nb2 = min(NB, nr);
-      for (int e = tid; e < NB * NB; e += kTailThreads) {
-        const int l = e / NB, c = e % NB;
+      // every global load of this step in flight before the first use: the block's 32 panel rows (column block kb) and the old
+      // values of its leading tile -- one L2 round trip instead of one per loop iteration
+      constexpr int NS = NB * NB / kTailThreads;                       // 4 staged entries per thread and matrix
+      constexpr int NLd = (NB * LD + kTailThreads - 1) / kTailThreads;  // 5 leading-tile entries per thread and matrix
+      double sa_[NS], sg_[NS], oa_[NLd], og_[NLd];
+#pragma unroll
+      for (int u = 0; u < NS; ++u) {
+        const int e = tid + u * kTailThreads, l = e / NB, c = e % NB;
         const bool in = (l < nb2 && c < nb);
-        DA[l * LD + c] = in ? A[(size_t)(r0 + l) * ld + kb + c] : 0.0;
-        DG[l * LD + c] = (in && !full) ? G[(size_t)(r0 + l) * ld + kb + c] : 0.0;
+        sa_[u] = in ? __ldcg(A + (size_t)(r0 + l) * ld + kb + c) : 0.0;
+        sg_[u] = (in && !full) ? __ldcg(G + (size_t)(r0 + l) * ld + kb + c) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < NLd; ++u) {
+        const int e = tid + u * kTailThreads, i = e / LD, j = e % LD;
+        const bool in = (e < NB * LD && i < nb2 && j <= i);
+        oa_[u] = in ? __ldcg(A + (size_t)(r0 + i) * ld + r0 + j) : 0.0;
+        og_[u] = (in && !full) ? __ldcg(G + (size_t)(r0 + i) * ld + r0 + j) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < NS; ++u) {
+        const int e = tid + u * kTailThreads, l = e / NB, c = e % NB;
+        DA[l * LD + c] = sa_[u];
+        DG[l * LD + c] = sg_[u];
       }
       __syncthreads();
+#pragma unroll 1
       for (int e = tid; e < NB * NB; e += kTailThreads) {  // X = rows * Linv^T (rows of a dropped pivot of Linv are zero)
         const int l = e / NB, j = e % NB;
-        double sa0 = 0.0, sa1 = 0.0, sg0 = 0.0, sg1 = 0.0;
-#pragma unroll 4
-        for (int c = 0; c < NB; c += 2) {
-          sa0 += DA[l * LD + c] * LIA[j * LD + c]; sa1 += DA[l * LD + c + 1] * LIA[j * LD + c + 1];
-          if (!full) { sg0 += DG[l * LD + c] * LIG[j * LD + c]; sg1 += DG[l * LD + c + 1] * LIG[j * LD + c + 1]; }
+        double sa[4] = {0.0, 0.0, 0.0, 0.0}, sg[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+        for (int c = 0; c < NB; c += 4) {
+          double a4[4], l4[4];
+          tf_ld4(DA + l * LD + c, a4); tf_ld4(LIA + j * LD + c, l4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sa[q] += a4[q] * l4[q];
+          if (!full) {
+            double g4[4], h4[4];
+            tf_ld4(DG + l * LD + c, g4); tf_ld4(LIG + j * LD + c, h4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sg[q] += g4[q] * h4[q];
+          }
         }
-        WB[l * LD + j] = sa0 + sa1;
-        DT[l * LD + j] = sg0 + sg1;
+        WB[l * LD + j] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+        DT[l * LD + j] = (sg[0] + sg[1]) + (sg[2] + sg[3]);
       }
       __syncthreads();
-      for (int e = tid; e < NB * LD; e += kTailThreads) {  // the next diagonal block = its leading tile of the trailing update
-        const int i = e / LD, j = e % LD;
+#pragma unroll
+      for (int u = 0; u < NLd; ++u) {  // the next diagonal block = its leading tile of the trailing update
+        const int e = tid + u * kTailThreads, i = e / LD, j = e % LD;
+        if (e >= NB * LD) break;
         double va = 0.0, vg = 0.0;
         if (i < nb2 && j <= i) {
-          double sa0 = 0.0, sa1 = 0.0, sg0 = 0.0, sg1 = 0.0;
-          const double oa = A[(size_t)(r0 + i) * ld + r0 + j], og = full ? 0.0 : G[(size_t)(r0 + i) * ld + r0 + j];
-#pragma unroll 4
-          for (int c = 0; c < NB; c += 2) {
-            sa0 += WB[i * LD + c] * WB[j * LD + c]; sa1 += WB[i * LD + c + 1] * WB[j * LD + c + 1];
-            if (!full) { sg0 += DT[i * LD + c] * DT[j * LD + c]; sg1 += DT[i * LD + c + 1] * DT[j * LD + c + 1]; }
+          double sa[4] = {0.0, 0.0, 0.0, 0.0}, sg[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+          for (int c = 0; c < NB; c += 4) {
+            double a4[4], b4[4];
+            tf_ld4(WB + i * LD + c, a4); tf_ld4(WB + j * LD + c, b4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sa[q] += a4[q] * b4[q];
+            if (!full) {
+              double g4[4], h4[4];
+              tf_ld4(DT + i * LD + c, g4); tf_ld4(DT + j * LD + c, h4);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) sg[q] += g4[q] * h4[q];
+            }
           }
-          va = oa - (sa0 + sa1);
-          vg = og - (sg0 + sg1);
+          va = oa_[u] - ((sa[0] + sa[1]) + (sa[2] + sa[3]));
+          vg = og_[u] - ((sg[0] + sg[1]) + (sg[2] + sg[3]));
         }
         DA[e] = va;
         DG[e] = vg;

@@ -163,7 +163,10 @@ int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap);
  *                  (15 + 6M <= 255; default on; 0 = always run it as a separate sweep -- same results up to rounding);
  *              4 = launch the update's kernels with programmatic dependent launch (default on);
  *              5 = Gram products of the compression on the FP64 tensor-core path (mma.sync m8n8k4 f64, SASS DMMA; default on;
- *                  0 = SIMT DFMA tiles -- same results to fp64 rounding) */
+ *                  0 = SIMT DFMA tiles -- same results to fp64 rounding);
+ *              6 = threads that work on one track in the feature kernel: 128 (a CTA per track: lowest latency), 64, or 32
+ *                  (a warp per track, two tracks per CTA: highest throughput); 0 = by batch size (default: 128 for one
+ *                  filter, 32 for a device batch).  The results are bit-identical for every value. */
 int msckf_b200_set_option(msckf_b200_engine* e, int key, double value);
 /* checkpoint / resume: copy the complete filter state of src into dst (same dtype and capacities) */
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src);

@@ -69,6 +69,7 @@ struct UpdArgs {
   double* Yq;            // [3N x c]  U_j^T D X_j - 1/2 (U_j^T D U_j) Z_j
   double* ur;            // [3N]      U_j^T r_j
   double *G1p, *G2p;     // split-K partials of the Gram products
+  double* bzp;           // split-K partials of Z^T (U^T r)  [nsplit][c], written by the diagonal tiles of the Gram kernel
   double *D1, *D2, *bb;  // per-clone 6x6 sums
   double *T2, *R2, *r2, *TP, *S2, *W, *G, *y, *dx, *idiag;
   int* keep;
@@ -88,6 +89,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }  // (REDUX)
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -36,6 +36,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define RC(call) do { int rc_ = (call); if (rc_ != 0) return rc_; } while (0)
 
 constexpr int kMaxSplit = 16;
+constexpr int kJacBatchGroup = 32;  // k_jac threads per track in a device batch (profiles/r02_*)
 constexpr int kTailCluster = 8;  // portable cluster size: the serial EKF tail runs on 8 SMs of one GPC
 constexpr size_t kSmemBudget = 220 * 1024;
 constexpr int kMaxClonesHard = mb::kMaxKeep;  // the keep list of prune() travels as a kernel argument
@@ -88,7 +89,7 @@ inline size_t tail_smem(int n, int kind) { return kind == 0 ? mb::tail_fused_sme
 
 // grid / shared-memory shape of one (batched) update: what a captured graph is valid for
 struct LaunchShape {
-  int nf, mode, tri_gx, jac_gx, bd_gx, gram_gx, gram_gy, asm_gx, rows_gx, gemm_g, syrk_gx, tail_mask, pdl, gram_mma;
+  int nf, mode, tri_gx, jac_gx, bd_gx, gram_gx, gram_gy, asm_gx, rows_gx, gemm_g, syrk_gx, tail_mask, pdl, gram_mma, jac_g;
   unsigned tri_smem, jac_smem, rows_smem, inj_smem, tail_smem[3];
   const void* args;  // device address of the UpdArgs array (moves only when the input arena is re-allocated)
   bool operator==(const LaunchShape& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
@@ -133,6 +134,7 @@ struct EngineBase {
   bool use_pdl = true;
   bool gram_mma = true;        // option 5: Gram products on the FP64 tensor-core path (DMMA) instead of SIMT DFMA tiles
   bool no_fused_tail = false;  // option 3 = 0: substitution as a separate sweep even where the fused form fits
+  int jac_group = 0;           // option 6: threads per track in k_jac (32 / 64 / 128; 0 = by batch size)
   int dtype = 0, device = 0, Mmax = 0, Tmax = 0, Omax = 0;
   int M = 0;
   double rank_thr = 1e-11;
@@ -277,10 +279,12 @@ struct Ctx : CtxBase {
   cudaEvent_t ev[kMaxEv] = {};
   const char* ev_name[kMaxEv] = {};
   int n_ev = 0;
+  int n_sm = 0;
 
   int init(int dev) {
     device = dev;
     CK(cudaSetDevice(device));
+    CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -362,7 +366,9 @@ struct Engine : EngineBase {
     static bool done = false;  // (per scalar type; the attribute is per function and device-wide)
     if (done) return 0;
     CK(cudaFuncSetAttribute(mb::k_tri<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_jac<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_jac<S, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_jac<S, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_jac<S, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_tail_fused<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_tail<S, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_tail<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
@@ -407,7 +413,7 @@ struct Engine : EngineBase {
     CK(cudaMalloc(&d_Yq, sizeof(double) * 3 * T * cmax));
     CK(cudaMalloc(&d_ur, sizeof(double) * 3 * T));
     CK(cudaMalloc(&d_G1p, sizeof(double) * kMaxSplit * cmax * cmax));
-    CK(cudaMalloc(&d_G2p, sizeof(double) * kMaxSplit * cmax * cmax));
+    CK(cudaMalloc(&d_G2p, sizeof(double) * (kMaxSplit * cmax * cmax + kMaxSplit * cmax)));  // + the Z^T u partials
     return 0;
   }
   void set_dims() {
@@ -585,7 +591,7 @@ struct Engine : EngineBase {
     a.cm_eff = p.d_cmeff; a.cm_ok = p.d_cm; a.tri_ok = p.d_tri; a.valid = p.d_valid; a.accept = p.d_accept; a.pfg = p.d_pfg; a.gamma = p.d_gamma;
     a.counter_snap = d_csnap; a.src = d_src; a.rows = d_rows; a.row_off = d_rowoff; a.done = d_done;
     a.Xg = d_Xg; a.rg = d_rg; a.Vg = d_Vg; a.taug = d_taug; a.Z = d_Z; a.Yq = d_Yq; a.ur = d_ur;
-    a.G1p = d_G1p; a.G2p = d_G2p; a.D1 = d_D1; a.D2 = d_D2; a.bb = d_bb;
+    a.G1p = d_G1p; a.G2p = d_G2p; a.bzp = d_G2p + (size_t)kMaxSplit * 6 * Mmax * 6 * Mmax; a.D1 = d_D1; a.D2 = d_D2; a.bb = d_bb;
     a.T2 = d_T2; a.R2 = d_R2; a.r2 = d_r2; a.TP = d_TP; a.S2 = d_S2; a.W = d_W; a.G = d_G; a.y = d_y; a.dx = d_dx; a.idiag = d_idiag;
     a.keep = d_keep;
     a.prof = profile ? d_prof : nullptr;
@@ -847,7 +853,7 @@ int Ctx<S>::launch() {
   LaunchShape sh;
   memset(&sh, 0, sizeof(sh));
   sh.nf = nf; sh.mode = mode; sh.args = d_args();
-  int Nmax = 0, Mmax_ = 0, Lm = 0, nmax_ = 0, nsplit = 1;
+  int Nmax = 0, Mmax_ = 0, Lm = 0, nmax_ = 0, nsplit = 1, jac_L = 0, jac_M = 0;
   for (int i = 0; i < nf; ++i) {
     const Plan<S>& p = plan[i];
     if (p.N == 0) continue;
@@ -855,7 +861,7 @@ int Ctx<S>::launch() {
     Nmax = std::max(Nmax, p.N); Mmax_ = std::max(Mmax_, a.M); Lm = std::max(Lm, p.Lmax); nmax_ = std::max(nmax_, a.n);
     nsplit = std::max(nsplit, a.nsplit);
     sh.tri_smem = std::max<unsigned>(sh.tri_smem, (unsigned)(16 + sizeof(S) * mb::kPoseStride * (size_t)a.M + sizeof(S) * 4 * 14 * (size_t)p.Lmax));
-    sh.jac_smem = std::max<unsigned>(sh.jac_smem, (unsigned)mb::jac_smem_bytes<S>(p.Lmax, a.M));
+    jac_L = std::max(jac_L, p.Lmax); jac_M = std::max(jac_M, a.M);
     sh.gram_mma |= a.gram_mma ? 2 : 1;  // which Gram kernels the batch needs
     if (mode != MSCKF_B200_TRIANGULATE) {
       sh.tail_mask |= 1 << a.tail_kind;
@@ -863,17 +869,22 @@ int Ctx<S>::launch() {
     }
   }
   if (Nmax == 0) return 0;  // nothing to do on the device
+  // k_jac: threads per track.  One filter: the whole CTA per track (latency).  A device batch: a warp per track, two tracks
+  // per 64-thread CTA (throughput: a track's serial sections no longer idle its CTA), widened while the CTA's groups do not fit.
+  sh.jac_g = eng[0]->jac_group ? eng[0]->jac_group : (nf > 1 ? kJacBatchGroup : 128);
+  while (sh.jac_g < 128 && mb::jac_smem_bytes<S>(jac_L, jac_M, sh.jac_g) > kSmemBudget) sh.jac_g *= 2;
+  sh.jac_smem = (unsigned)mb::jac_smem_bytes<S>(jac_L, jac_M, sh.jac_g);
   if (sh.tri_smem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_tri shared memory");
   if (mode != MSCKF_B200_TRIANGULATE && sh.jac_smem > kSmemBudget) return fail(MSCKF_B200_ERR_CAPACITY, "k_jac shared memory");
   const int Nr = (Nmax + 15) & ~15;  // rounded track count: kernels exit on blockIdx >= their filter's own N
   sh.tri_smem = (sh.tri_smem + 1023) & ~1023u; sh.jac_smem = (sh.jac_smem + 1023) & ~1023u;
   if (sh.tri_smem > kSmemBudget) sh.tri_smem = (unsigned)kSmemBudget;
   if (sh.jac_smem > kSmemBudget) sh.jac_smem = (unsigned)kSmemBudget;
-  sh.tri_gx = (Nr + 3) / 4; sh.jac_gx = Nr; sh.rows_gx = Nr; sh.bd_gx = Mmax_;
+  sh.tri_gx = (Nr + 3) / 4; sh.jac_gx = Nr / (sh.jac_g == 128 ? 1 : 2); sh.rows_gx = Nr; sh.bd_gx = Mmax_;
   const int c = nmax_ - mb::kImuDim, ntile = (c + mb::GT - 1) / mb::GT;
   sh.gram_gx = ntile * (ntile + 1) / 2; sh.gram_gy = nsplit;
   sh.asm_gx = std::min(592, (nmax_ * nmax_ + 255) / 256);
-  sh.rows_smem = (unsigned)(sizeof(double) * 12 * (size_t)((Lm + 7) & ~7));
+  sh.rows_smem = (unsigned)(sizeof(double) * mb::rows_smem_doubles((Lm + 7) & ~7));
   sh.gemm_g = (nmax_ + 31) / 32;
   sh.syrk_gx = sh.gemm_g * (sh.gemm_g + 1) / 2;
   sh.inj_smem = (unsigned)(sizeof(double) * nmax_);
@@ -963,7 +974,8 @@ int Ctx<S>::run_kernels(const LaunchShape& sh) {
     mark("k_tri");
   }
   if (sh.mode != MSCKF_B200_TRIANGULATE) {
-    CK(launch_k(mb::k_jac<S>, dim3(sh.jac_gx, 1, nf), dim3(mb::JT), sh.jac_smem, stream, pdl && sh.mode != MSCKF_B200_RESIDUALIZE, 1, A));
+    auto kj = sh.jac_g == 32 ? mb::k_jac<S, 32> : (sh.jac_g == 64 ? mb::k_jac<S, 64> : mb::k_jac<S, 128>);
+    CK(launch_k(kj, dim3(sh.jac_gx, 1, nf), dim3(sh.jac_g == 32 ? 64 : 128), sh.jac_smem, stream, pdl && sh.mode != MSCKF_B200_RESIDUALIZE, 1, A));
     launches++;
     mark("k_jac");
     // k_blockdiag and k_gram both depend on k_jac only: two branches (a fork / join in the captured graph)
@@ -1099,6 +1111,7 @@ int msckf_b200_create(const msckf_b200_config* cfg, msckf_b200_engine** out) {
   if (getenv("MSCKF_B200_NO_PDL")) b->use_pdl = false;
   if (getenv("MSCKF_B200_NO_DMMA")) b->gram_mma = false;
   if (getenv("MSCKF_B200_NO_FUSED_TAIL")) b->no_fused_tail = true;
+  if (const char* g = getenv("MSCKF_B200_JAC_GROUP")) { const int v = atoi(g); if (v == 32 || v == 64 || v == 128) b->jac_group = v; }
   b->dtype = cfg->dtype; b->device = cfg->device; b->Mmax = cfg->max_clones; b->Tmax = cfg->max_tracks; b->Omax = cfg->max_obs;
   int rc = (cfg->dtype == MSCKF_B200_F32) ? static_cast<Engine<float>*>(b)->alloc() : static_cast<Engine<double>*>(b)->alloc();
   if (rc != 0) { delete b; return rc; }
@@ -1224,6 +1237,12 @@ int msckf_b200_set_option(msckf_b200_engine* e, int key, double value) {
   if (key == 3) { e->impl->no_fused_tail = value == 0; return 0; }
   if (key == 4) { e->impl->use_pdl = value != 0; return 0; }
   if (key == 5) { e->impl->gram_mma = value != 0; return 0; }
+  if (key == 6) {
+    const int g = (int)value;
+    if (g != 0 && g != 32 && g != 64 && g != 128) return fail(MSCKF_B200_ERR_ARG, "option 6: 0, 32, 64 or 128");
+    e->impl->jac_group = g;
+    return 0;
+  }
   return fail(MSCKF_B200_ERR_ARG, "unknown option");
 }
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src) { return dst->impl->copy_from(src->impl); }

@@ -247,37 +247,71 @@ __global__ void __launch_bounds__(WPB * 32) k_tri(const UpdArgs<S>* __restrict__
 // packed lower-triangular symmetric storage
 __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
 
-constexpr int JT = 128;  // threads per feature in k_jac
+constexpr int JT = 128;  // most threads a CTA of k_jac has (see JGrp)
 
-template <class T>
-__device__ __forceinline__ T block_sum(T v, T* red /*[JT/32]*/) {
+// A track is worked on by a GROUP of G threads (G = 128: the whole CTA -- lowest latency, used for a single filter;
+// G = 64 / 32: two / four tracks per CTA, a warp (pair) each -- the CTA barriers between the phases of a track become
+// named barriers / __syncwarp, so a track's serial sections (the QR warp, the panels of the gate Cholesky) no longer idle
+// the warps of the same CTA: they belong to other tracks.  Used for device batches, where throughput is what counts.)
+template <int G>
+struct JGrp {
+  static_assert(G == 32 || G == 64 || G == 128, "group size");
+  // G = 32 runs in CTAs of 64 threads (two tracks): the finer the CTA, the more tracks fit the SM's shared memory (18 at L = 30)
+  static constexpr int CT = (G == 32) ? 64 : 128, NW = G / 32, TPC = CT / G;
+  __device__ static __forceinline__ void sync(int grp) {
+    if (G == CT) __syncthreads();
+    else if (G == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" : : "r"(grp + 1), "r"(G) : "memory");
+  }
+};
+
+// sum over the group; red: the CTA's CT/32 slots (one per warp)
+template <int G, class T>
+__device__ __forceinline__ T group_sum(T v, T* red, int grp) {
   v = warp_sum(v);
-  __syncthreads();
+  if (G == 32) return v;
+  const int w0 = grp * JGrp<G>::NW;
+  JGrp<G>::sync(grp);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  T t = red[0];
+  JGrp<G>::sync(grp);
+  T t = red[w0];
 #pragma unroll
-  for (int w = 1; w < JT / 32; ++w) t += red[w];
+  for (int w = 1; w < JGrp<G>::NW; ++w) t += red[w0 + w];
   return t;
 }
 
-// three sums at once (one pair of barriers)
-__device__ __forceinline__ void block_sum3(double v[3], double* red /*[3 * JT/32]*/) {
+// Floating-point sums over a track's group, bit-identical for every group size: the terms are dealt to 128 VIRTUAL threads
+// (virtual thread v = 32 w + lane owns the terms v, v + 128, ...), every virtual warp w is reduced by shuffles, and the four
+// warp sums are added in the order ((s0 + s1) + s2) + s3.  A group of G threads plays 4 / (G/32) virtual warps per warp, so a
+// device batch (G = 32) rounds exactly like the same filter run alone (G = 128).
+// part(v, p): the K partial sums of virtual thread v;  red: [TPC][4][K] shared slots.
+template <int G, int K, class T, class F>
+__device__ __forceinline__ void group_vsum(T (&out)[K], F part, T* red, int grp) {
+  constexpr int NW = JGrp<G>::NW, R = 4 / NW;
+  const int lane = threadIdx.x & 31, gw = (threadIdx.x % G) >> 5;
+  T s[R][K];
 #pragma unroll
-  for (int q = 0; q < 3; ++q) v[q] = warp_sum(v[q]);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) {
+  for (int q = 0; q < R; ++q) {
+    T p[K];
+    part(32 * (gw + NW * q) + lane, p);
 #pragma unroll
-    for (int q = 0; q < 3; ++q) red[3 * (threadIdx.x >> 5) + q] = v[q];
+    for (int k = 0; k < K; ++k) s[q][k] = warp_sum(p[k]);
   }
-  __syncthreads();
+  if (G == 32) {
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    double t = red[q];
-#pragma unroll
-    for (int w = 1; w < JT / 32; ++w) t += red[3 * w + q];
-    v[q] = t;
+    for (int k = 0; k < K; ++k) out[k] = ((s[0][k] + s[R > 1 ? 1 : 0][k]) + s[R > 2 ? 2 : 0][k]) + s[R > 3 ? 3 : 0][k];
+    return;
   }
+  JGrp<G>::sync(grp);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+#pragma unroll
+      for (int k = 0; k < K; ++k) red[(grp * 4 + gw + NW * q) * K + k] = s[q][k];
+  }
+  JGrp<G>::sync(grp);
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = ((red[(grp * 4 + 0) * K + k] + red[(grp * 4 + 1) * K + k]) + red[(grp * 4 + 2) * K + k]) + red[(grp * 4 + 3) * K + k];
 }
 
 __device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
@@ -289,7 +323,7 @@ __device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
   v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
 }
 
-// ---- gate Cholesky, blocked by panels of 8 columns, all JT threads of the CTA.
+// ---- gate Cholesky, blocked by panels of 8 columns, all G threads of the track's group.
 // The matrix is the trailing block [3:, 3:] of the packed-lower 2L x 2L array Y (rho = 2L - 3 rows); the right-hand side
 // r[3:] rides along as row rho.  Only y = L^-1 r is wanted (gamma = |y|^2), so the factor itself is never written back.
 // Per panel:  (1) every thread that owns a row loads the 8 x 8 diagonal micro-block and factorises it redundantly in registers (static
@@ -300,12 +334,12 @@ __device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
 // the lower triangle, one barrier.  57 pivots cost 8 panels x 2 barriers instead of 57 dependent warp-wide steps
 // (round 1: one warp, shuffle + shared-memory round trip per pivot, ~350 ns each = 20 us of k_jac's 55).
 constexpr int kPW = 8;
-template <class S>
-__device__ __forceinline__ bool gate_chol_blocked(S* __restrict__ Y, S* __restrict__ r, int L2, S* __restrict__ PnT, int Rp, int* s_fail) {
-  const int rho = L2 - 3, R = rho + 1, tid = threadIdx.x;
+template <class S, int G>
+__device__ __forceinline__ bool gate_chol_blocked(S* __restrict__ Y, S* __restrict__ r, int L2, S* __restrict__ PnT, int Rp, int* s_fail, int grp) {
+  const int rho = L2 - 3, R = rho + 1, tid = threadIdx.x % G;
   if (tid == 0) *s_fail = 0;
-  for (int e = tid; e < kPW * Rp; e += JT) PnT[e] = S(0);  // (rows R..Rp-1 of a partial tile must read as zero)
-  __syncthreads();
+  for (int e = tid; e < kPW * Rp; e += G) PnT[e] = S(0);  // (rows R..Rp-1 of a partial tile must read as zero)
+  JGrp<G>::sync(grp);
   for (int p0 = 0; p0 < rho; p0 += kPW) {
     const int w = min(kPW, rho - p0);
     // (1) diagonal micro-block: lower triangle in registers, identity padding beyond w -- only in the threads that own a row
@@ -333,7 +367,7 @@ __device__ __forceinline__ bool gate_chol_blocked(S* __restrict__ Y, S* __restri
       }
       if (!ok && tid == 0) *s_fail = 1;  // (thread 0 always owns a row: the right-hand side is row rho >= q0)
       // (2) rows below the micro-block, and the right-hand side
-      for (int i = q0 + tid; i < R; i += JT) {
+      for (int i = q0 + tid; i < R; i += G) {
         S x[kPW];
         if (i < rho) {
           const S* row = Y + pk(3 + i, 3 + p0);
@@ -357,13 +391,13 @@ __device__ __forceinline__ bool gate_chol_blocked(S* __restrict__ Y, S* __restri
         }
       }
     }
-    __syncthreads();
+    JGrp<G>::sync(grp);
     if (*s_fail) return false;  // a non-positive pivot (uniform: read after the barrier)
     // (4) trailing update: rows q0..R-1, columns q0..rho-1, lower triangle, 4 x 4 tiles (q0 is a multiple of 8 here)
     const int nrows = R - q0;
     if (nrows > 1) {
       const int nt = (nrows + 3) >> 2, ntile = nt * (nt + 1) / 2;
-      for (int q = tid; q < ntile; q += JT) {
+      for (int q = tid; q < ntile; q += G) {
         int ti, tj;
         tri_tile_index(q, ti, tj);
         const int r0 = q0 + 4 * ti, c0 = q0 + 4 * tj;
@@ -396,32 +430,44 @@ __device__ __forceinline__ bool gate_chol_blocked(S* __restrict__ Y, S* __restri
         }
       }
     }
-    __syncthreads();
+    JGrp<G>::sync(grp);
   }
   return true;
 }
 
+// shared memory of one track's group (rounded to 16 bytes), in units of S:
+//   X 12L | r 2L | V 6L | WF 12L (+ slack) | Ypacked L(2L+1)
+// with two aliases: U (fp64 [2L][3], the first 3 columns of the feature's Q) lives at the start of WF until the compact
+// outputs are written (before the two-sided transform fills W and F), and the gate Cholesky's transposed panel PnT
+// (8 x Rp, Rp = (2L + 1) & ~3, 16-byte aligned) lives on V | WF once the transform is done.
 template <class S>
-__host__ __device__ inline size_t jac_smem_bytes(int L, int M, bool /*unused: kept for the call sites*/ = true) {
-  // bar 16 | poses M*8 S | U64 6L doubles | X 12L | r 2L | V 6L | W 6L | F 6L | Ypacked L(2L+1)  (S) | pad |
-  // PnT 8 x Rp (S): the gate Cholesky's transposed panel, Rp = (2L - 2 + 3) & ~3
-  return 16 + sizeof(S) * kPoseStride * (size_t)M + 16 + sizeof(double) * 6 * (size_t)L +
-         sizeof(S) * ((size_t)32 * L + (size_t)L * (2 * L + 1)) + 32 + sizeof(S) * (size_t)kPW * (size_t)((2 * L + 1) & ~3) + 16;
+__host__ __device__ inline size_t jac_vwf_elems(int L) { return (size_t)(18 * L > 16 * L + 12 ? 18 * L : 16 * L + 12); }
+template <class S>
+__host__ __device__ inline size_t jac_group_bytes(int L) {
+  const size_t b = sizeof(S) * ((size_t)14 * L + jac_vwf_elems<S>(L) + (size_t)L * (2 * L + 1));
+  return (b + 15) & ~(size_t)15;
+}
+// whole CTA: bar 16 | poses M*8 S (groups of 64 / 128 threads only: a single warp reads its few poses from global) | pad |
+// tpc groups (sized by the launch's longest track)
+template <class S>
+__host__ __device__ inline size_t jac_smem_bytes(int L, int M, int g) {
+  const int tpc = (g == 128) ? 1 : 2;
+  return 16 + (g == 32 ? 0 : sizeof(S) * kPoseStride * (size_t)M) + 16 + (size_t)tpc * jac_group_bytes<S>(L);
 }
 
 // Ordered stacking (msckf.h:433-445): the exclusive prefix sum of the accepted blocks' row counts, computed by whichever
 // CTA of k_jac finishes last (ticket counter) -- a separate 1-CTA kernel for 300 integers cost 8 us of launch latency.
-template <class S>
-__device__ __forceinline__ void jac_finish(const UpdArgs<S>& a) {
+template <class S, int CT>
+__device__ __forceinline__ void jac_finish(const UpdArgs<S>& a, int n_cta /* CTAs of this filter that arrive here */) {
   __shared__ int s_last;
-  __shared__ int s_part[JT / 32];
+  __shared__ int s_part[CT / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __syncthreads();
-  if (tid == 0) { __threadfence(); s_last = (atomicAdd(a.done, 1u) == (unsigned)a.n_tracks - 1u) ? 1 : 0; }
+  if (tid == 0) { __threadfence(); s_last = (atomicAdd(a.done, 1u) == (unsigned)n_cta - 1u) ? 1 : 0; }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const int N = a.n_tracks, per = (N + JT - 1) / JT;
+  const int N = a.n_tracks, per = (N + CT - 1) / CT;
   const int b = min(N, tid * per), e = min(N, b + per);
   int sum = 0;
   for (int k = b; k < e; ++k) sum += __ldcg(a.rows + k);
@@ -433,31 +479,25 @@ __device__ __forceinline__ void jac_finish(const UpdArgs<S>& a) {
   int run = incl - sum;
   for (int w = 0; w < warp; ++w) run += s_part[w];
   for (int k = b; k < e; ++k) { a.row_off[k] = run; run += __ldcg(a.rows + k); }
-  if (tid == JT - 1) { a.row_off[N] = run; a.m_out[0] = run; a.m_out[2] = 0; /* status: set by k_syrk / k_inject */ }
+  if (tid == CT - 1) { a.row_off[N] = run; a.m_out[0] = run; a.m_out[2] = 0; /* status: set by k_syrk / k_inject */ }
   if (tid == 0) *a.done = 0u;
 }
 
-// calcResidual + calcMeasJacobian + gatingTest for one feature per CTA (JT threads), with loop A's bookkeeping
-// (msckf.h:352-399: valid flags, num_feature_tracks_residualized_, and the p_f_G_vec index of :419) folded into
-// the prologue.  mode 0: marginalize semantics; mode 1: every track valid at its given position.
-template <class S>
-__global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args) {
-  pdl_wait();
-  const UpdArgs<S>& a = args[blockIdx.z];
-  if ((int)blockIdx.x >= a.n_tracks) return;
+// calcResidual + calcMeasJacobian + gatingTest for one feature per group of G threads (JT / G features per CTA), with
+// loop A's bookkeeping (msckf.h:352-399: valid flags, num_feature_tracks_residualized_, and the p_f_G_vec index of :419)
+// folded into the prologue.  mode 0: marginalize semantics; mode 1: every track valid at its given position.
+// Inside: `tid`, `warp` are relative to the group; every barrier is the group's.
+template <class S, int G>
+__device__ __forceinline__ void jac_track(const UpdArgs<S>& a, const int t, const int grp, unsigned char* __restrict__ gmem_sm,
+                                          const S* __restrict__ poses, double* redd, S* reds, int* redi) {
+  using Gp = JGrp<G>;
   DevState<S>* st_rw = a.st;
   const int mode = (a.mode == 2) ? 1 : 0;  // MSCKF_B200_RESIDUALIZE: every track valid at its given position
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  S* poses = reinterpret_cast<S*>(smem_raw + 16);
-  stage_table_tma(poses, a.poses, (unsigned)(a.M * kPoseStride * sizeof(S)), bar);
-  __shared__ double redd[JT / 32];
-  __shared__ S reds[JT / 32];
-  __shared__ int redi[JT / 32];
-  __shared__ int s_he, s_valid, s_src, s_pushed_t;
-  __shared__ unsigned long long s_cnt;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int t = blockIdx.x;
+  __shared__ int s_he_[Gp::TPC], s_valid_[Gp::TPC], s_src_[Gp::TPC], s_pushed_t_[Gp::TPC];
+  __shared__ unsigned long long s_cnt_[Gp::TPC];
+  int &s_he = s_he_[grp], &s_valid = s_valid_[grp], &s_src = s_src_[grp], &s_pushed_t = s_pushed_t_[grp];
+  unsigned long long& s_cnt = s_cnt_[grp];
+  const int tid = threadIdx.x % G, lane = tid & 31;
   const int N = a.n_tracks;
   const int c = 6 * a.M;
   int prof_i = 0;
@@ -481,25 +521,18 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
       s_he = k;
       s_cnt = counter;
     }
-    __syncthreads();
+    Gp::sync(grp);
     const int he = s_he;
     // pushed(k): the track pushed a position into p_f_G_vec (msckf.h:374)
     int before = 0, total = 0, nvalid_tail = 0;
-    for (int k = tid; k < N; k += JT) {
+    for (int k = tid; k < N; k += G) {
       const int cm = a.cm_ok[k];
       const int pushed = (k < he) ? 1 : cm;
       total += pushed;
       if (k < t) before += pushed;
       if (k >= he && cm && a.tri_ok[k]) nvalid_tail++;
     }
-    auto isum = [&](int v) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      __syncthreads();
-      if (lane == 0) redi[tid >> 5] = v;
-      __syncthreads();
-      return redi[0] + redi[1] + redi[2] + redi[3];
-    };
+    auto isum = [&](int v) { return group_sum<G>(v, redi, grp); };
     total = isum(total);
     before = isum(before);
     nvalid_tail = isum(nvalid_tail);
@@ -525,7 +558,7 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
       if (t == 0) st_rw->num_residualized = s_cnt + (unsigned long long)nvalid_tail;
     }
   }
-  __syncthreads();
+  Gp::sync(grp);
   stamp();  // bookkeeping
   const int o0 = a.obs_off[t], L = a.obs_off[t + 1] - o0, L2 = 2 * L;
   const int valid = (L >= 2) ? s_valid : 0, src = s_src;  // fewer than two observations: no null space (2L - 3 < 1)
@@ -533,22 +566,19 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
   double* Yr = a.Yq + (size_t)3 * t * c;
   if (tid == 0) { a.valid[t] = valid; a.src[t] = src; }
   if (!valid) {  // not residualised: contributes nothing
-    for (int k = tid; k < 3 * c; k += JT) { Zr[k] = 0.0; Yr[k] = 0.0; }
+    for (int k = tid; k < 3 * c; k += G) { Zr[k] = 0.0; Yr[k] = 0.0; }
     if (tid == 0) { a.accept[t] = 0; a.gamma[t] = S(0); a.rows[t] = 0; a.ur[3 * t] = a.ur[3 * t + 1] = a.ur[3 * t + 2] = 0.0; }
-    jac_finish(a);
     return;
   }
   // ------------------------------------------------------------------ shared-memory carve-up
-  unsigned char* wp = smem_raw + 16 + sizeof(S) * kPoseStride * (size_t)a.M;
-  wp = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(wp) + 15) & ~uintptr_t(15));
-  double* U = reinterpret_cast<double*>(wp);  // [2L][3] fp64
-  S* X = reinterpret_cast<S*>(U + 3 * L2);
+  S* X = reinterpret_cast<S*>(gmem_sm);
   S* r = X + 12 * L;
   S* V = r + L2;
   S* wv = V + 3 * L2;   // [2L][3]  W = Y V
   S* Fv = wv + 3 * L2;  // [2L][3]  F of the two-sided transform
-  S* Y = Fv + 3 * L2;
-  S* PnT = reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(Y + (size_t)L * (L2 + 1)) + 15) & ~uintptr_t(15));  // [8][Rp]
+  double* U = reinterpret_cast<double*>(wv);  // [2L][3] fp64; dead before W is written
+  S* Y = V + jac_vwf_elems<S>(L);
+  S* PnT = reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(V) + 15) & ~uintptr_t(15));  // [8][Rp]; V, W, F are dead by then
   const int Rp = (L2 + 1) & ~3;  // >= rho + 1 = 2L - 2, multiple of 4
   const int* idx = a.clone_idx + o0;
   const S* z = a.obs + 2 * (size_t)o0;
@@ -557,7 +587,7 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
   const S* pfsrc = mode ? (a.pfg_given + 3 * t) : (a.pfg + 3 * src);
   const S pf[3] = {pfsrc[0], pfsrc[1], pfsrc[2]};
   // ---- residual + measurement Jacobian blocks with the observability projection (msckf.h:915-950, 960-978)
-  for (int i = tid; i < L; i += JT) {
+  for (int i = tid; i < L; i += G) {
     const S* ps = poses + kPoseStride * idx[i];
     S C[9];
     quat_to_rot(ps, C);
@@ -604,14 +634,17 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
       }
     }
   }
-  __syncthreads();
+  Gp::sync(grp);
   stamp();  // X, r
   // ---- warp 0: column-pivoted Householder QR of H_f (2L x 3) -- the trailing 2L-3 columns of Q are A_j
   // (msckf.h:954-955) -- then U, U^T r, r~ and the compact-WY factor, all warp-synchronous (shuffle reductions, no CTA
   // barriers).  Warps 1..3 meanwhile: Y = X P_sub X^T.
-  __shared__ S s_tau[3];
-  __shared__ S s_T[9];
-  __shared__ double s_urv[3];
+  __shared__ S s_tau_[Gp::TPC][3];
+  __shared__ S s_T_[Gp::TPC][9];
+  __shared__ double s_urv_[Gp::TPC][3];
+  S* s_tau = s_tau_[grp];
+  S* s_T = s_T_[grp];
+  double* s_urv = s_urv_[grp];
   const int warp = tid >> 5;
   if (warp == 0) {
     S tau[3];
@@ -739,13 +772,14 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
       s_T[6] = S(0); s_T[7] = S(0); s_T[8] = t22;
       s_tau[0] = t00; s_tau[1] = t11; s_tau[2] = t22;
     }
-  } else {
+  }
+  if (G == 32 || warp != 0) {  // (a single-warp group does both, one after the other)
     // ---- gating (msckf.h:1103-1124): gamma = r_o^T (H_o P H_o^T + u_var I)^-1 r_o with H_o = (Q^T X)[3:]
     // Y = X P_sub X^T, symmetric 2L x 2L, packed lower
     const int npairs = L * (L + 1) / 2;
     const S* P = a.P;
     const int ldp = a.ldp;
-    for (int p = tid - 32; p < npairs; p += JT - 32) {
+    for (int p = (G == 32) ? tid : tid - 32; p < npairs; p += (G == 32) ? 32 : G - 32) {
       int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
       while (i * (i + 1) / 2 > p) --i;
       while ((i + 1) * (i + 2) / 2 <= p) ++i;
@@ -778,14 +812,50 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
       if (i != k) Y[pk(2 * i, 2 * k + 1)] = y01;
     }
   }
-  __syncthreads();
+  Gp::sync(grp);
   stamp();  // QR, U, r~ (warp 0) | Y pairs (warps 1..3)
   const double urv[3] = {s_urv[0], s_urv[1], s_urv[2]};
+  // ---- compact outputs for the Gram stage, written as if accepted (U's shared memory is about to become W | F); a rejected
+  // track zeroes them again after the gate
+  for (int k = tid; k < 3 * c; k += G) { Zr[k] = 0.0; Yr[k] = 0.0; }
+  double Mm[6];  // M = U^T D U (3x3 symmetric), D = diag(u_var, v_var, u_var, ...)
+  const double du = (double)st->u_var, dv = (double)st->v_var;
+  group_vsum<G, 6>(Mm, [&](int v, double (&p)[6]) {
+    for (int k = 0; k < 6; ++k) p[k] = 0.0;
+    for (int row = v; row < L2; row += 128) {
+      const double dd = (row & 1) ? dv : du;
+      const double u0 = U[3 * row], u1 = U[3 * row + 1], u2 = U[3 * row + 2];
+      p[0] += dd * u0 * u0; p[1] += dd * u0 * u1; p[2] += dd * u0 * u2;
+      p[3] += dd * u1 * u1; p[4] += dd * u1 * u2; p[5] += dd * u2 * u2;
+    }
+  }, redd, grp);
+  const double M3[3][3] = {{Mm[0], Mm[1], Mm[2]}, {Mm[1], Mm[3], Mm[4]}, {Mm[2], Mm[4], Mm[5]}};
+  Gp::sync(grp);
+  {
+    for (int e = tid; e < L * 6; e += G) {
+      const int i = e / 6, b = e % 6;
+      const int col = 6 * idx[i] + b;
+      const double xa = X[12 * i + b], xb = X[12 * i + 6 + b];
+      double zb[3], yb[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const double ua = U[3 * (2 * i) + q], ub = U[3 * (2 * i + 1) + q];
+        zb[q] = ua * xa + ub * xb;
+        yb[q] = du * ua * xa + dv * ub * xb;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        Zr[(size_t)q * c + col] = zb[q];
+        Yr[(size_t)q * c + col] = yb[q] - 0.5 * (M3[q][0] * zb[0] + M3[q][1] * zb[1] + M3[q][2] * zb[2]);
+      }
+    }
+  }
+  Gp::sync(grp);  // U is dead: W, F take its place
   // ---- two-sided transform in one pass: Q^T Y Q = Y - (V F^T + F V^T),  F = W T - V (T^T B T) / 2,  W = Y V,  B = V^T W
   S* Wv = wv;  // [L2][3]  (wv and pv are contiguous: 2 * L2 each, >= 3 * L2 + ... see jac_smem_bytes)
   {
     // W = Y V: two threads per row (row part | column part of the packed symmetric storage)
-    for (int base = 0; base < L2; base += JT / 2) {
+    for (int base = 0; base < L2; base += G / 2) {
       const int ar = base + (tid >> 1), h = tid & 1;
       S w0 = 0, w1 = 0, w2 = 0;
       if (ar < L2) {
@@ -800,7 +870,7 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
       if (ar < L2 && h == 0) { Wv[3 * ar] = w0; Wv[3 * ar + 1] = w1; Wv[3 * ar + 2] = w2; }
     }
   }
-  __syncthreads();
+  Gp::sync(grp);
   if (warp == 0) {
     S Bm[6] = {0, 0, 0, 0, 0, 0};  // B = V^T W (symmetric): 00 01 02 11 12 22
     for (int row = lane; row < L2; row += 32) {
@@ -833,11 +903,11 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
         Fv[3 * row + j] = (w0 * Tm[0][j] + w1 * Tm[1][j] + w2 * Tm[2][j]) - (v0 * G3[0][j] + v1 * G3[1][j] + v2 * G3[2][j]);
     }
   }
-  __syncthreads();
+  Gp::sync(grp);
   // only the trailing block [3:, 3:] is used below: S = (Q^T Y Q)[3:,3:] + u_var I, in place in the packed array
   const S uvar = st->u_var;
   const int rho = L2 - 3;
-  for (int ar = 3 + warp; ar < L2; ar += JT / 32) {  // one row per warp, lanes along the row
+  for (int ar = 3 + warp; ar < L2; ar += G / 32) {  // one row per warp, lanes along the row
     const S va0 = V[3 * ar], va1 = V[3 * ar + 1], va2 = V[3 * ar + 2];
     const S fa0 = Fv[3 * ar], fa1 = Fv[3 * ar + 1], fa2 = Fv[3 * ar + 2];
     for (int b = 3 + lane; b <= ar; b += 32) {
@@ -845,49 +915,26 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
       Y[pk(ar, b)] = (b == ar) ? val + uvar : val;
     }
   }
-  __syncthreads();
+  Gp::sync(grp);
   stamp();  // two-sided transform
   // Cholesky with the right-hand side r~[3:] riding along as an extra row: y = L^-1 r~, gamma = |y|^2
-  __shared__ int s_chol_fail;
-  const bool chol_ok = gate_chol_blocked<S>(Y, r, L2, PnT, Rp, &s_chol_fail);
-  S gacc = 0;
-  for (int j = 3 + tid; j < L2; j += JT) gacc += r[j] * r[j];
+  __shared__ int s_chol_fail[Gp::TPC];
+  const bool chol_ok = gate_chol_blocked<S, G>(Y, r, L2, PnT, Rp, &s_chol_fail[grp], grp);
   (void)rho;
-  S gam = block_sum(gacc, reds);
+  S gam1[1];
+  group_vsum<G, 1>(gam1, [&](int v, S (&p)[1]) {
+    p[0] = S(0);
+    for (int j = 3 + v; j < L2; j += 128) p[0] += r[j] * r[j];
+  }, reds, grp);
+  S gam = gam1[0];
   const int acc = chol_ok && (gam < st->chi2[L]);  // table[dof+1], dof = L-1 (msckf.h:433,:1117)
   if (!chol_ok) gam = S(1e30);
   stamp();  // Cholesky + gamma
-  // ---- compact outputs for the Gram stage
-  for (int k = tid; k < 3 * c; k += JT) { Zr[k] = 0.0; Yr[k] = 0.0; }
-  double Mm[6] = {0, 0, 0, 0, 0, 0};  // M = U^T D U (3x3 symmetric), D = diag(u_var, v_var, u_var, ...)
-  const double du = (double)st->u_var, dv = (double)st->v_var;
-  for (int row = tid; row < L2; row += JT) {
-    const double dd = (row & 1) ? dv : du;
-    const double u0 = U[3 * row], u1 = U[3 * row + 1], u2 = U[3 * row + 2];
-    Mm[0] += dd * u0 * u0; Mm[1] += dd * u0 * u1; Mm[2] += dd * u0 * u2;
-    Mm[3] += dd * u1 * u1; Mm[4] += dd * u1 * u2; Mm[5] += dd * u2 * u2;
-  }
+  if (!acc) {
+    for (int e = tid; e < L * 6; e += G) {
+      const int col = 6 * idx[e / 6] + e % 6;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) Mm[k] = block_sum(Mm[k], redd);
-  const double M3[3][3] = {{Mm[0], Mm[1], Mm[2]}, {Mm[1], Mm[3], Mm[4]}, {Mm[2], Mm[4], Mm[5]}};
-  __syncthreads();
-  if (acc) {
-    for (int e = tid; e < L * 6; e += JT) {
-      const int i = e / 6, b = e % 6;
-      const int col = 6 * idx[i] + b;
-      const double xa = X[12 * i + b], xb = X[12 * i + 6 + b];
-      double zb[3], yb[3];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const double ua = U[3 * (2 * i) + q], ub = U[3 * (2 * i + 1) + q];
-        zb[q] = ua * xa + ub * xb;
-        yb[q] = du * ua * xa + dv * ub * xb;
-      }
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        Zr[(size_t)q * c + col] = zb[q];
-        Yr[(size_t)q * c + col] = yb[q] - 0.5 * (M3[q][0] * zb[0] + M3[q][1] * zb[1] + M3[q][2] * zb[2]);
-      }
+      for (int q = 0; q < 3; ++q) { Zr[(size_t)q * c + col] = 0.0; Yr[(size_t)q * c + col] = 0.0; }
     }
   }
   if (tid == 0) {
@@ -898,7 +945,32 @@ __global__ void __launch_bounds__(JT) k_jac(const UpdArgs<S>* __restrict__ args)
   }
   stamp();  // outputs
   if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[40 + prof_i] = 0ull;
-  jac_finish(a);
+}
+
+template <class S, int G>
+__global__ void __launch_bounds__(JGrp<G>::CT, (G == 32) ? (sizeof(S) == 4 ? 9 : 5) : (sizeof(S) == 4 ? 5 : 3)) k_jac(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  const UpdArgs<S>& a = args[blockIdx.z];
+  constexpr int TPC = JGrp<G>::TPC, CT = JGrp<G>::CT;
+  const int N = a.n_tracks;
+  if ((int)blockIdx.x * TPC >= N) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const S* poses = a.poses;
+  unsigned char* wp = smem_raw + 16;
+  if (G != 32) {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    S* ps = reinterpret_cast<S*>(smem_raw + 16);
+    stage_table_tma(ps, a.poses, (unsigned)(a.M * kPoseStride * sizeof(S)), bar);
+    poses = ps;
+    wp += sizeof(S) * kPoseStride * (size_t)a.M;
+  }
+  __shared__ double redd[TPC * 4 * 6];
+  __shared__ S reds[TPC * 4];
+  __shared__ int redi[CT / 32];
+  const int grp = threadIdx.x / G, t = blockIdx.x * TPC + grp;
+  wp = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(wp) + 15) & ~uintptr_t(15));
+  if (t < N) jac_track<S, G>(a, t, grp, wp + (size_t)grp * jac_group_bytes<S>(a.Lmax), poses, redd, reds, redi);
+  jac_finish<S, CT>(a, (N + TPC - 1) / TPC);
 }
 
 }  // namespace mb

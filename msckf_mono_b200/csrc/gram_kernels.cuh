@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(256) k_gram(const UpdArgs<S>* __restrict__ arg
   double* __restrict__ G1p = A.G1p;
   double* __restrict__ G2p = A.G2p;
   __shared__ double sZa[GK][GT + 1], sZb[GK][GT + 1], sYa[GK][GT + 1], sYb[GK][GT + 1];
+  __shared__ double sU[GK], sBz[8][GT + 1];
+  const double* __restrict__ ur = A.ur;
   // decode the (ta <= tb) tile pair
   const int ntile = (c + GT - 1) / GT;
   if ((int)blockIdx.x >= ntile * (ntile + 1) / 2 || (int)blockIdx.y >= A.nsplit || A.n_tracks == 0 || A.gram_mma) return;
@@ -45,7 +47,13 @@ __global__ void __launch_bounds__(256) k_gram(const UpdArgs<S>* __restrict__ arg
   const int k0 = split * kchunk, k1 = min(K, k0 + kchunk);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 2x2 outputs each
   double a1[2][2] = {{0, 0}, {0, 0}}, a2[2][2] = {{0, 0}, {0, 0}};
+  // the diagonal tiles also accumulate this split's part of Z^T (U^T r) for their 32 columns (beta of the header): the
+  // operand is in shared memory anyway; thread = (column, one of 8 k-groups)
+  const bool diag = ta == tb;
+  const int bc = threadIdx.x & 31, bg = threadIdx.x >> 5;
+  double bz = 0.0;
   for (int kb = k0; kb < k1; kb += GK) {
+    if (diag && threadIdx.x < GK) sU[threadIdx.x] = (kb + (int)threadIdx.x < k1) ? ur[kb + threadIdx.x] : 0.0;
     for (int e = threadIdx.x; e < GK * GT; e += 256) {
       const int kk = e / GT, cc = e % GT;
       const int k = kb + kk;
@@ -65,7 +73,18 @@ __global__ void __launch_bounds__(256) k_gram(const UpdArgs<S>* __restrict__ arg
       a2[0][0] += za0 * yb0 + ya0 * zb0; a2[0][1] += za0 * yb1 + ya0 * zb1;
       a2[1][0] += za1 * yb0 + ya1 * zb0; a2[1][1] += za1 * yb1 + ya1 * zb1;
     }
+    if (diag) bz += sZa[2 * bg][bc] * sU[2 * bg] + sZa[2 * bg + 1][bc] * sU[2 * bg + 1];
     __syncthreads();
+  }
+  if (diag) {
+    sBz[bg][bc] = bz;
+    __syncthreads();
+    if (bg == 0 && ta * GT + bc < c) {
+      double t = 0.0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) t += sBz[g][bc];
+      A.bzp[(size_t)split * c + ta * GT + bc] = t;
+    }
   }
   double* o1 = G1p + (size_t)split * c * c;
   double* o2 = G2p + (size_t)split * c * c;
@@ -98,6 +117,8 @@ __global__ void __launch_bounds__(128) k_gram_mma(const UpdArgs<S>* __restrict__
   const double* __restrict__ Z = A.Z;
   const double* __restrict__ Yq = A.Yq;
   __shared__ double sZa[GK][GL], sZb[GK][GL], sYa[GK][GL], sYb[GK][GL];
+  __shared__ double sU[GK], sBz[4][GT + 1];
+  const double* __restrict__ ur = A.ur;
   const int ntile = (c + GT - 1) / GT;
   if ((int)blockIdx.x >= ntile * (ntile + 1) / 2 || (int)blockIdx.y >= A.nsplit || A.n_tracks == 0 || !A.gram_mma) return;
   int pidx = blockIdx.x, ta = 0;
@@ -113,7 +134,10 @@ __global__ void __launch_bounds__(128) k_gram_mma(const UpdArgs<S>* __restrict__
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) { c1[i][j][0] = c1[i][j][1] = 0.0; c2[i][j][0] = c2[i][j][1] = 0.0; }
+  const bool diag = ta == tb;  // (see k_gram: this split's part of Z^T (U^T r); thread = (column, one of 4 k-groups))
+  double bzs = 0.0;
   for (int kb = k0; kb < k1; kb += GK) {
+    if (diag && tid < GK) sU[tid] = (kb + tid < k1) ? ur[kb + tid] : 0.0;
     for (int e = tid; e < GK * GT; e += 128) {
       const int kk = e / GT, cc = e % GT;
       const int k = kb + kk;
@@ -141,7 +165,16 @@ __global__ void __launch_bounds__(128) k_gram_mma(const UpdArgs<S>* __restrict__
           dmma(c2[i][j], ay[i], bz[j]);
         }
     }
+    if (diag) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bzs += sZa[4 * warp + q][lane] * sU[4 * warp + q];
+    }
     __syncthreads();
+  }
+  if (diag) {
+    sBz[warp][lane] = bzs;
+    __syncthreads();
+    if (warp == 0 && ta * GT + lane < c) A.bzp[(size_t)split * c + ta * GT + lane] = (sBz[0][lane] + sBz[1][lane]) + (sBz[2][lane] + sBz[3][lane]);
   }
   double* o1 = A.G1p + (size_t)split * c * c;
   double* o2 = A.G2p + (size_t)split * c * c;
@@ -217,19 +250,14 @@ __global__ void __launch_bounds__(128) k_blockdiag(const UpdArgs<S>* __restrict_
 
 // Assemble T'' (n x n), r'' (n), R'' (n x n) except the <=15 head rows (k_head fills those afterwards).
 template <class S>
-__global__ void __launch_bounds__(256) k_assemble(const UpdArgs<S>* __restrict__ args) {
-  pdl_wait();
-  pdl_launch();
-  const UpdArgs<S>& A = args[blockIdx.z];
+__device__ __forceinline__ void assemble_work(const UpdArgs<S>& A, int cta, int ncta) {
   if (A.n_tracks == 0) return;
-  const int n = A.n, ld = A.ld, K = A.K, nsplit = A.nsplit;
+  const int n = A.n, ld = A.ld, nsplit = A.nsplit;
   const double* __restrict__ G1p = A.G1p;
   const double* __restrict__ G2p = A.G2p;
   const double* __restrict__ D1 = A.D1;
   const double* __restrict__ D2 = A.D2;
   const double* __restrict__ bb = A.bb;
-  const double* __restrict__ Z = A.Z;
-  const double* __restrict__ ur = A.ur;
   const int* __restrict__ m_in = A.m_out;
   double* __restrict__ T2 = A.T2;
   double* __restrict__ R2 = A.R2;
@@ -237,7 +265,7 @@ __global__ void __launch_bounds__(256) k_assemble(const UpdArgs<S>* __restrict__
   const int c = n - kImuDim;
   const bool full = *m_in <= n;  // m <= n: plain uncompressed update, all rows explicit (k_rows), no Gram part
   const size_t total = (size_t)n * n;
-  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+  for (size_t e = (size_t)cta * 256 + threadIdx.x; e < total; e += (size_t)ncta * 256) {
     const int a = (int)(e / n), b = (int)(e % n);
     double tv = 0.0, rv = 0.0;
     if (!full && a >= kImuDim && b >= kImuDim) {
@@ -255,26 +283,24 @@ __global__ void __launch_bounds__(256) k_assemble(const UpdArgs<S>* __restrict__
     T2[(size_t)a * ld + b] = tv;
     R2[(size_t)a * ld + b] = rv;
   }
-  // beta = blk(sum X^T r) - Z^T (U^T r): 32 columns x 8 k-groups per CTA, reduced through shared memory
-  __shared__ double part[8][33];
-  const int al = threadIdx.x & 31, kg = threadIdx.x >> 5;
-  for (int a0 = blockIdx.x * 32; a0 < n; a0 += gridDim.x * 32) {
-    const int a = a0 + al;
-    double s = 0.0;
-    if (!full && a < n && a >= kImuDim) {
+  // beta = blk(sum X^T r) - Z^T (U^T r); the second term arrives as split-K partials from the Gram kernel's diagonal tiles
+  const double* __restrict__ bzp = A.bzp;
+  for (int a = cta * 256 + threadIdx.x; a < n; a += ncta * 256) {
+    double v = 0.0;
+    if (!full && a >= kImuDim) {
       const int ac = a - kImuDim;
-      for (int k = kg; k < K; k += 8) s += Z[(size_t)k * c + ac] * ur[k];
-    }
-    part[kg][al] = s;
-    __syncthreads();
-    if (kg == 0 && a < n) {
       double t = 0.0;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) t += part[g][al];
-      r2[a] = (!full && a >= kImuDim) ? bb[a - kImuDim] - t : 0.0;
+      for (int s = 0; s < nsplit; ++s) t += bzp[(size_t)s * c + ac];
+      v = bb[ac] - t;
     }
-    __syncthreads();
+    r2[a] = v;
   }
+}
+template <class S>
+__global__ void __launch_bounds__(256) k_assemble(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  assemble_work(args[blockIdx.z], blockIdx.x, gridDim.x);
 }
 
 // Explicit stacked rows ("head rows"), one CTA per feature.
@@ -285,13 +311,24 @@ __global__ void __launch_bounds__(256) k_assemble(const UpdArgs<S>* __restrict__
 //            Gram part is switched off (k_assemble).
 // Row t of feature j is A_j(:,t)^T [X_j | r_j] with A_j(:,t) = Q e_{3+t},  Q = H0 H1 H2 = I - V T V^T (compact WY,
 // exact reflectors tau_k = 2 / v_k^T v_k in fp64): every entry of Q costs O(1) from V (2L x 3) and T (3 x 3).
+constexpr int kRowsFixed = 6 + 9 + 9 + 3 + 3 * kImuDim;  // s_g | s_T | s_Wd | s_s | s_adu
+__host__ __device__ inline size_t rows_smem_doubles(int Lmax) { return (size_t)kRowsFixed + 12 * (size_t)Lmax; }
+// is track j a head track of this update (explicit rows)?  uniform per CTA
 template <class S>
-__global__ void __launch_bounds__(128) k_rows(const UpdArgs<S>* __restrict__ args) {
-  pdl_wait();
-  pdl_launch();
-  const UpdArgs<S>& A = args[blockIdx.z];
-  extern __shared__ double sh[];  // V[2L][3] | W[2L][3]
-  const int j = blockIdx.x;
+__device__ __forceinline__ bool rows_is_head(const UpdArgs<S>& A, int j) {
+  if (j >= A.n_tracks || !A.accept[j]) return false;
+  const int m = *A.m_out;
+  return A.row_off[j] < ((m <= A.n) ? m : kImuDim);
+}
+template <class S>
+__device__ __forceinline__ void rows_work(const UpdArgs<S>& A, int j, double* __restrict__ smem) {
+  const int nthr = blockDim.x;
+  double* s_g = smem;
+  double* s_T = s_g + 6;
+  double* s_Wd = s_T + 9;
+  double* s_s = s_Wd + 9;
+  double (*s_adu)[3] = reinterpret_cast<double (*)[3]>(s_s + 3);
+  double* sh = smem + kRowsFixed;  // V[2L][3] | W[2L][3]
   if (j >= A.n_tracks) return;
   const int n = A.n, ld = A.ld;
   const int* __restrict__ obs_off = A.obs_off;
@@ -320,8 +357,7 @@ __global__ void __launch_bounds__(128) k_rows(const UpdArgs<S>* __restrict__ arg
   const int tid = threadIdx.x;
   double* V = sh;
   double* W = sh + 3 * L2;
-  __shared__ double s_g[6], s_T[9], s_Wd[9], s_s[3], s_adu[kImuDim][3];
-  for (int e = tid; e < 3 * L2; e += 128) V[e] = (double)Vg[3 * 2 * (size_t)o0 + e];
+  for (int e = tid; e < 3 * L2; e += nthr) V[e] = (double)Vg[3 * 2 * (size_t)o0 + e];
   __syncthreads();
   if (tid < 6) {  // v_k^T v_l : (0,0) (1,1) (2,2) (0,1) (0,2) (1,2)
     const int ka[6] = {0, 1, 2, 0, 0, 1}, kb[6] = {0, 1, 2, 1, 2, 2};
@@ -341,7 +377,7 @@ __global__ void __launch_bounds__(128) k_rows(const UpdArgs<S>* __restrict__ arg
     for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) s_T[3 * k + l] = T[k][l];
   }
   __syncthreads();
-  for (int a = tid; a < L2; a += 128)
+  for (int a = tid; a < L2; a += nthr)
     for (int l = 0; l < 3; ++l) W[3 * a + l] = V[3 * a] * s_T[l] + V[3 * a + 1] * s_T[3 + l] + V[3 * a + 2] * s_T[6 + l];
   __syncthreads();
   if (tid < 9) {  // Wd = sum_a d_a w_a^T w_a
@@ -370,7 +406,7 @@ __global__ void __launch_bounds__(128) k_rows(const UpdArgs<S>* __restrict__ arg
     return ((a == b) ? 1.0 : 0.0) - (W[3 * a] * V[3 * b] + W[3 * a + 1] * V[3 * b + 1] + W[3 * a + 2] * V[3 * b + 2]);
   };
   // r rows and the R_o block of this feature restricted to the explicit rows
-  for (int e = tid; e < nh * (nh + 1); e += 128) {
+  for (int e = tid; e < nh * (nh + 1); e += nthr) {
     const int t = e / (nh + 1), u = e % (nh + 1);
     const int b = 3 + t;
     if (u == nh) {
@@ -382,7 +418,7 @@ __global__ void __launch_bounds__(128) k_rows(const UpdArgs<S>* __restrict__ arg
   if (!full && tid < nh * 3) s_adu[tid / 3][tid % 3] = qdq(3 + tid / 3, tid % 3);  // A_h^T D U
   __syncthreads();
   // H rows (and, when compressing, the coupling rows R_hH = A_h^T D Pi_j X_j)
-  for (int e = tid; e < nh * L * 6; e += 128) {
+  for (int e = tid; e < nh * L * 6; e += nthr) {
     const int t = e / (L * 6), rem = e % (L * 6), i = rem / 6, bb = rem % 6;
     const int b = 3 + t;
     const int col = 6 * clone_idx[o0 + i] + bb;
@@ -396,6 +432,13 @@ __global__ void __launch_bounds__(128) k_rows(const UpdArgs<S>* __restrict__ arg
       R2[(size_t)(kImuDim + col) * ld + (h0 + t)] = rv;
     }
   }
+}
+template <class S>
+__global__ void __launch_bounds__(128) k_rows(const UpdArgs<S>* __restrict__ args) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ double rows_sm[];
+  rows_work(args[blockIdx.z], blockIdx.x, rows_sm);
 }
 
 }  // namespace mb

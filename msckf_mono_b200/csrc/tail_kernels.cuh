@@ -16,11 +16,14 @@ namespace mb {
 // (measured at config B: 27 us with 64 threads, 18 us with 128, see profiles/).
 // LA(k, a) / LB(k, b) fetch operand elements, EPI(a, b, acc) stores.
 constexpr int kGemmThreads = 256;
+constexpr int kGemmSmemDoubles = 2 * 1024 + (kGemmThreads / 64 - 1) * 1024;  // two operand slabs + the partial sums of three k-groups
 template <class LoadA, class LoadB, class Epi>
-__device__ __forceinline__ void gemm_tile32(int n, int k_begin, int a0, int b0, LoadA LA, LoadB LB, Epi EPI) {
+__device__ __forceinline__ void gemm_tile32(double* __restrict__ sm /* kGemmSmemDoubles, 16-byte aligned */, int n, int k_begin, int a0, int b0,
+                                            LoadA LA, LoadB LB, Epi EPI) {
   constexpr int kParts = kGemmThreads / 64, kPer = 32 / kParts, kFetch = 1024 / kGemmThreads;
-  __shared__ __align__(16) double sA[32][32], sB[32][32];
-  __shared__ double red[kParts - 1][16][64];
+  double (*sA)[32] = reinterpret_cast<double (*)[32]>(sm);
+  double (*sB)[32] = reinterpret_cast<double (*)[32]>(sm + 1024);
+  double (*red)[16][64] = reinterpret_cast<double (*)[16][64]>(sm + 2048);
   const int tid = threadIdx.x;
   const int part = tid >> 6, t = tid & 63;
   const int tx = t & 7, ty = t >> 3;
@@ -81,19 +84,38 @@ __device__ __forceinline__ void gemm_tile32(int n, int k_begin, int a0, int b0, 
 
 // TP[a][b] = sum_k T2[a][k] * P[k][b]      (T2 columns < 15 are zero)
 template <class S>
+__device__ __forceinline__ void gemm_tp_tile(const UpdArgs<S>& A, double* __restrict__ sm, int ty, int tx) {
+  const int n = A.n, ld = A.ld, ldp = A.ldp;
+  const double* __restrict__ T2 = A.T2;
+  const S* __restrict__ P = A.P;
+  double* __restrict__ TP = A.TP;
+  gemm_tile32(sm, n, kImuDim, ty * 32, tx * 32,
+              [&](int k, int a) { return T2[(size_t)a * ld + k]; },
+              [&](int k, int b) { return (double)P[(size_t)k * ldp + b]; },
+              [&](int a, int b, double v) { TP[(size_t)a * ld + b] = v; });
+}
+// S2[a][b] = sum_k TP[a][k] * T2[b][k] + R2[a][b]
+template <class S>
+__device__ __forceinline__ void gemm_s_tile(const UpdArgs<S>& A, double* __restrict__ sm, int ty, int tx) {
+  const int n = A.n, ld = A.ld;
+  const double* __restrict__ TP = A.TP;
+  const double* __restrict__ T2 = A.T2;
+  const double* __restrict__ R2 = A.R2;
+  double* __restrict__ S2 = A.S2;
+  gemm_tile32(sm, n, kImuDim, ty * 32, tx * 32,  // T2 columns < 15 are zero
+              [&](int k, int a) { return TP[(size_t)a * ld + k]; },
+              [&](int k, int b) { return T2[(size_t)b * ld + k]; },
+              [&](int a, int b, double v) { S2[(size_t)a * ld + b] = v + R2[(size_t)a * ld + b]; });
+}
+template <class S>
 __global__ void __launch_bounds__(kGemmThreads) k_gemm_tp(const UpdArgs<S>* __restrict__ args) {
   pdl_wait();
   pdl_launch();
   const UpdArgs<S>& A = args[blockIdx.z];
   const int n = A.n, ld = A.ld, ldp = A.ldp;
   if ((int)blockIdx.x * 32 >= n || (int)blockIdx.y * 32 >= n || A.n_tracks == 0) return;
-  const double* __restrict__ T2 = A.T2;
-  const S* __restrict__ P = A.P;
-  double* __restrict__ TP = A.TP;
-  gemm_tile32(n, kImuDim, blockIdx.y * 32, blockIdx.x * 32,
-              [&](int k, int a) { return T2[(size_t)a * ld + k]; },
-              [&](int k, int b) { return (double)P[(size_t)k * ldp + b]; },
-              [&](int a, int b, double v) { TP[(size_t)a * ld + b] = v; });
+  __shared__ __align__(16) double sm[kGemmSmemDoubles];
+  gemm_tp_tile(A, sm, blockIdx.y, blockIdx.x);
 }
 
 // S2[a][b] = sum_k TP[a][k] * T2[b][k] + R2[a][b]
@@ -104,14 +126,8 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_s(const UpdArgs<S>* __res
   const UpdArgs<S>& A = args[blockIdx.z];
   const int n = A.n, ld = A.ld;
   if ((int)blockIdx.x * 32 >= n || (int)blockIdx.y * 32 >= n || A.n_tracks == 0) return;
-  const double* __restrict__ TP = A.TP;
-  const double* __restrict__ T2 = A.T2;
-  const double* __restrict__ R2 = A.R2;
-  double* __restrict__ S2 = A.S2;
-  gemm_tile32(n, kImuDim, blockIdx.y * 32, blockIdx.x * 32,  // T2 columns < 15 are zero
-              [&](int k, int a) { return TP[(size_t)a * ld + k]; },
-              [&](int k, int b) { return T2[(size_t)b * ld + k]; },
-              [&](int a, int b, double v) { S2[(size_t)a * ld + b] = v + R2[(size_t)a * ld + b]; });
+  __shared__ __align__(16) double sm[kGemmSmemDoubles];
+  gemm_s_tile(A, sm, blockIdx.y, blockIdx.x);
 }
 
 // P <- P - W^T W (lower-triangular tile pairs; written in the filter precision, exactly symmetric by construction), and in
@@ -132,7 +148,8 @@ __global__ void __launch_bounds__(kGemmThreads) k_syrk(const UpdArgs<S>* __restr
   int pidx = blockIdx.x, ta = 0;
   while (pidx >= ta + 1) { pidx -= ta + 1; ++ta; }  // (ta >= tb)
   const int tb = pidx;
-  gemm_tile32(n, 0, ta * 32, tb * 32,
+  __shared__ __align__(16) double sm[kGemmSmemDoubles];
+  gemm_tile32(sm, n, 0, ta * 32, tb * 32,
               [&](int k, int a) { return Wm[(size_t)k * ld + a]; },
               [&](int k, int b) { return Wm[(size_t)k * ld + b]; },
               [&](int a, int b, double v) {

@@ -189,6 +189,27 @@ def test_gram_on_fp64_tensor_cores_matches_simt_tiles():
     pc.check("gram_mma_vs_simt_300x30", pc.run_case("gram_mma_vs_simt_300x30"))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_track_group_sizes_of_the_feature_kernel_are_bit_identical(dtype):
+    """engine option 6: k_jac works on a track with a group of 128 (one filter), 64 or 32 threads (device batches).  The
+    floating-point sums are dealt to 128 virtual threads whatever the group, so all three give the same bits -- which is
+    what lets a batch reproduce the filter run alone.  Config B (60 rows per track: more than one virtual warp)."""
+    from msckf_mono_b200 import capi
+    wl = synth.make_window_workload(n_features=300, n_clones=30, seq=1)
+    out = []
+    for g in (128, 64, 32):
+        f = make_engine(dtype, max_clones=40, max_tracks=512, max_obs=512 * 30)
+        synth.drive(f, wl, marginalize_last=False)
+        capi.Engine(dtype, borrowed=f.engineHandle()).set_option(6, float(g))
+        f.marginalize()
+        rep = f.lastReport()
+        out.append((f.getCovariance(), rep["gamma"].copy(), rep["accepted"].copy(), f.getImuState()["p_I_G"].copy()))
+    assert out[0][2].sum() > 250
+    for o in out[1:]:
+        for a, b in zip(out[0], o):
+            assert np.array_equal(a, b)
+
+
 def test_batched_entry_point_matches_individual_updates():
     """`msckf_mono_marginalize_batch` (host work on several threads, one stream per filter) gives bit-identical filters to
     calling marginalize() one by one."""

@@ -156,6 +156,11 @@ int msckf_b200_set_covariance(msckf_b200_engine* e, const void* in);
 int msckf_b200_get_counters(msckf_b200_engine* e, long long* counters);
 /* last delta-x (fp64), returns its length */
 int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap);
+/* diagnostics of the last update's rank decision: for every index of the compressed system, the pivot of the basis Gram matrix
+ * relative to its original diagonal (the squared sine against the span of the previous basis vectors) at the moment it was
+ * compared with the rank threshold (option 0).  Directions in the null space of H_o show up as rounding noise here; the gap
+ * between that noise and the smallest kept pivot is the margin of the decision.  Returns 15 + 6 M. */
+int msckf_b200_rank_pivots(msckf_b200_engine* e, double* out, int cap);
 /* option keys: 0 = rank threshold of the compression (relative pivot of the basis Gram matrix = squared sine to the span of the previous basis vectors, default 1e-11);
  *              1 = record per-kernel CUDA events in _launch (profiling aid, default off);
  *              2 = replay the update's kernel sequence as a CUDA graph when the batch signature repeats (default on);

@@ -220,6 +220,11 @@ class Engine:
         check(lib().msckf_b200_update(self.h, C.c_int(mode), C.byref(batch.c), C.byref(rep)), "msckf_b200_update")
         return {"m": rep.m, "rank": rep.rank, "accepted": acc[:batch.n_tracks]}
 
+    def rank_pivots(self):
+        buf = (C.c_double * 2048)()
+        n = check(lib().msckf_b200_rank_pivots(self.h, buf, C.c_int(2048)), "msckf_b200_rank_pivots")
+        return np.array(buf[:n])
+
     def set_option(self, key, value):
         check(lib().msckf_b200_set_option(self.h, C.c_int(key), C.c_double(value)), "msckf_b200_set_option")
 

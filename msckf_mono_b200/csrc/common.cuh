@@ -72,6 +72,7 @@ struct UpdArgs {
   double* bzp;           // split-K partials of Z^T (U^T r)  [nsplit][c], written by the diagonal tiles of the Gram kernel
   double *D1, *D2, *bb;  // per-clone 6x6 sums
   double *T2, *R2, *r2, *TP, *S2, *W, *G, *y, *dx, *idiag;
+  double* pivr;          // [n] diagnostics: Gamma's pivot / its original diagonal at the moment of the keep / drop decision
   int* keep;
   unsigned long long* prof;  // optional: %globaltimer stamps (profiling aid)
 };

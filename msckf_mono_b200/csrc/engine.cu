@@ -79,7 +79,8 @@ inline size_t tail_legacy_smem(int n, int NB) {
   return sizeof(double) * ((size_t)2 * NB * (NB + 1) + 2 + (size_t)2 * NB * ldt + ((n + 1) & ~1) + 2 * NB) + 64;
 }
 inline int pick_tail(int n, bool no_fused) {
-  const bool fused = (n + 1 + kTailCluster - 1) / kTailCluster <= 32 && mb::tail_fused_smem_bytes(n) <= kSmemBudget && !no_fused;
+  const bool fused = (n + 1 + kTailCluster - 2) / (kTailCluster - 1) <= 32 &&  // (right-hand-side columns per worker CTA)
+                     mb::tail_fused_smem_bytes(n) <= kSmemBudget && !no_fused;
   if (fused) return 0;
   if (tail_legacy_smem(n, 32) <= kSmemBudget) return 1;
   if (tail_legacy_smem(n, 16) <= kSmemBudget) return 2;
@@ -89,7 +90,7 @@ inline size_t tail_smem(int n, int kind) { return kind == 0 ? mb::tail_fused_sme
 
 // grid / shared-memory shape of one (batched) update: what a captured graph is valid for
 struct LaunchShape {
-  int nf, mode, tri_gx, jac_gx, bd_gx, gram_gx, gram_gy, asm_gx, rows_gx, gemm_g, syrk_gx, tail_mask, pdl, gram_mma, jac_g;
+  int nf, mode, tri_gx, jac_gx, bd_gx, gram_gx, gram_gy, asm_gx, rows_gx, gemm_g, syrk_gx, tail_mask, pdl, gram_mma, jac_g, tail_nch;
   unsigned tri_smem, jac_smem, rows_smem, inj_smem, tail_smem[3];
   const void* args;  // device address of the UpdArgs array (moves only when the input arena is re-allocated)
   bool operator==(const LaunchShape& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
@@ -122,6 +123,7 @@ struct EngineBase {
   virtual int set_covariance(const void*) = 0;
   virtual int get_counters(long long*) = 0;
   virtual int last_dx(double*, int) = 0;
+  virtual int rank_pivots(double*, int) = 0;
   virtual int copy_from(const EngineBase*) = 0;
   virtual int sync() = 0;
   virtual int input_buffer(int, int, msckf_b200_tracks*) = 0;
@@ -134,10 +136,11 @@ struct EngineBase {
   bool use_pdl = true;
   bool gram_mma = true;        // option 5: Gram products on the FP64 tensor-core path (DMMA) instead of SIMT DFMA tiles
   bool no_fused_tail = false;  // option 3 = 0: substitution as a separate sweep even where the fused form fits
+  int tail_chains = 0;         // option 7: CTAs running the tail's chains of diagonal blocks (1, 2; 0 = 2 where the device takes clusters of 9)
   int jac_group = 0;           // option 6: threads per track in k_jac (32 / 64 / 128; 0 = by batch size)
   int dtype = 0, device = 0, Mmax = 0, Tmax = 0, Omax = 0;
   int M = 0;
-  double rank_thr = 1e-11;
+  double rank_thr = 1e-9;
   long long launches = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
   CtxBase* group = nullptr;  // the batch this engine belongs to (nullptr: none)
@@ -353,7 +356,7 @@ struct Engine : EngineBase {
   S *d_Xg = nullptr, *d_rg = nullptr, *d_Vg = nullptr, *d_taug = nullptr;
   double *d_Z = nullptr, *d_Yq = nullptr, *d_ur = nullptr, *d_G1p = nullptr, *d_G2p = nullptr, *d_D1 = nullptr, *d_D2 = nullptr,
          *d_bb = nullptr, *d_T2 = nullptr, *d_R2 = nullptr, *d_r2 = nullptr, *d_TP = nullptr, *d_S2 = nullptr, *d_W = nullptr, *d_G = nullptr,
-         *d_y = nullptr, *d_dx = nullptr, *d_idiag = nullptr;
+         *d_y = nullptr, *d_dx = nullptr, *d_idiag = nullptr, *d_pivr = nullptr;
   mb::DevState<S>* h_st = nullptr;
   int nmax = 0, ldp = 0, ld = 0;
   bool initialized = false;
@@ -362,6 +365,7 @@ struct Engine : EngineBase {
   CtxBase* solo_ctx() override { return &solo; }
   void drop_graphs() override { solo.drop_graphs(); if (group) static_cast<Ctx<S>*>(group)->drop_graphs(); }
 
+  static int& tail9_clusters() { static int v = 0; return v; }  // co-resident clusters of 9 (0: not available)
   static int set_func_attrs() {
     static bool done = false;  // (per scalar type; the attribute is per function and device-wide)
     if (done) return 0;
@@ -369,7 +373,20 @@ struct Engine : EngineBase {
     CK(cudaFuncSetAttribute(mb::k_jac<S, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_jac<S, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_jac<S, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    CK(cudaFuncSetAttribute(mb::k_tail_fused<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_tail_fused<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    CK(cudaFuncSetAttribute(mb::k_tail_fused<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    // the two-chain form runs in clusters of 9 (2 chain CTAs + 7 workers): a non-portable size; use it where the device takes it
+    if (cudaFuncSetAttribute(mb::k_tail_fused<S, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kTailCluster + 1, 1, 1); cfg.blockDim = dim3(mb::kTailThreads); cfg.dynamicSmemBytes = kSmemBudget;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = kTailCluster + 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, mb::k_tail_fused<S, 2>, &cfg) == cudaSuccess && ncl > 0) tail9_clusters() = ncl;
+    }
+    cudaGetLastError();
     CK(cudaFuncSetAttribute(mb::k_tail<S, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_tail<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     done = true;
@@ -378,7 +395,7 @@ struct Engine : EngineBase {
 
   // ---- allocation: resident state (sized by Mmax), per-window workspaces (Mmax), per-batch workspaces (Tmax, Omax, Mmax)
   void free_window() {
-    for (double** p : {&d_T2, &d_R2, &d_TP, &d_S2, &d_W, &d_G, &d_r2, &d_idiag, &d_y, &d_dx, &d_D1, &d_D2, &d_bb}) { if (*p) cudaFree(*p); *p = nullptr; }
+    for (double** p : {&d_T2, &d_R2, &d_TP, &d_S2, &d_W, &d_G, &d_r2, &d_idiag, &d_pivr, &d_y, &d_dx, &d_D1, &d_D2, &d_bb}) { if (*p) cudaFree(*p); *p = nullptr; }
     if (d_keep) { cudaFree(d_keep); d_keep = nullptr; }
   }
   void free_batchws() {
@@ -392,6 +409,8 @@ struct Engine : EngineBase {
     CK(cudaMalloc(&d_G, sizeof(double) * std::max((size_t)ld * nmax, (size_t)4 * 32 * 34 + (size_t)64 * (ld + 4))));
     CK(cudaMalloc(&d_r2, sizeof(double) * nmax));
     CK(cudaMalloc(&d_idiag, sizeof(double) * 2 * nmax));
+    CK(cudaMalloc(&d_pivr, sizeof(double) * 2 * nmax));  // pivots | original diagonal
+    CK(cudaMemsetAsync(d_pivr, 0, sizeof(double) * 2 * nmax, stream));
     CK(cudaMalloc(&d_y, sizeof(double) * nmax));
     CK(cudaMalloc(&d_dx, sizeof(double) * nmax));
     CK(cudaMemsetAsync(d_dx, 0, sizeof(double) * nmax, stream));
@@ -592,7 +611,7 @@ struct Engine : EngineBase {
     a.counter_snap = d_csnap; a.src = d_src; a.rows = d_rows; a.row_off = d_rowoff; a.done = d_done;
     a.Xg = d_Xg; a.rg = d_rg; a.Vg = d_Vg; a.taug = d_taug; a.Z = d_Z; a.Yq = d_Yq; a.ur = d_ur;
     a.G1p = d_G1p; a.G2p = d_G2p; a.bzp = d_G2p + (size_t)kMaxSplit * 6 * Mmax * 6 * Mmax; a.D1 = d_D1; a.D2 = d_D2; a.bb = d_bb;
-    a.T2 = d_T2; a.R2 = d_R2; a.r2 = d_r2; a.TP = d_TP; a.S2 = d_S2; a.W = d_W; a.G = d_G; a.y = d_y; a.dx = d_dx; a.idiag = d_idiag;
+    a.T2 = d_T2; a.R2 = d_R2; a.r2 = d_r2; a.TP = d_TP; a.S2 = d_S2; a.W = d_W; a.G = d_G; a.y = d_y; a.dx = d_dx; a.idiag = d_idiag; a.pivr = d_pivr;
     a.keep = d_keep;
     a.prof = profile ? d_prof : nullptr;
   }
@@ -684,6 +703,15 @@ struct Engine : EngineBase {
     return 0;
   }
 
+  int rank_pivots(double* out, int cap) override {
+    CK(cudaSetDevice(device));
+    const int n = 15 + 6 * M;
+    std::vector<double> tmp(2 * (size_t)n);
+    CK(cudaMemcpyAsync(tmp.data(), d_pivr, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int i = 0; i < std::min(n, cap); ++i) out[i] = tmp[n + i] > 0.0 ? tmp[i] / tmp[n + i] : 0.0;
+    return n;
+  }
   int last_dx(double* out, int cap) override {
     CK(cudaSetDevice(device));
     const int n = 15 + 6 * M;
@@ -889,6 +917,7 @@ int Ctx<S>::launch() {
   sh.syrk_gx = sh.gemm_g * (sh.gemm_g + 1) / 2;
   sh.inj_smem = (unsigned)(sizeof(double) * nmax_);
   sh.pdl = (eng[0]->use_pdl && !profile()) ? 1 : 0;
+  sh.tail_nch = (eng[0]->tail_chains == 1 || Engine<S>::tail9_clusters() == 0) ? 1 : 2;
   const bool want_graph = eng[0]->use_graph && !profile();
   if (want_graph) {
     for (auto& g : graphs)
@@ -1003,7 +1032,11 @@ int Ctx<S>::run_kernels(const LaunchShape& sh) {
     mark("k_gemm_s");
     launches += 2;
     // rank decision + Cholesky + substitution: one thread-block cluster per filter (kernels of a kind no member uses are skipped)
-    if (sh.tail_mask & 1) { CK(launch_k(mb::k_tail_fused<S>, dim3(kTailCluster, 1, nf), dim3(mb::kTailThreads), sh.tail_smem[0], stream, pdl, kTailCluster, A)); launches++; }
+    if (sh.tail_mask & 1) {
+      if (sh.tail_nch == 2) CK(launch_k(mb::k_tail_fused<S, 2>, dim3(kTailCluster + 1, 1, nf), dim3(mb::kTailThreads), sh.tail_smem[0], stream, pdl, kTailCluster + 1, A));
+      else CK(launch_k(mb::k_tail_fused<S, 1>, dim3(kTailCluster, 1, nf), dim3(mb::kTailThreads), sh.tail_smem[0], stream, pdl, kTailCluster, A));
+      launches++;
+    }
     if (sh.tail_mask & 2) { CK(launch_k(mb::k_tail<S, 32>, dim3(kTailCluster, 1, nf), dim3(mb::kTailThreads), sh.tail_smem[1], stream, pdl, kTailCluster, A)); launches++; }
     if (sh.tail_mask & 4) { CK(launch_k(mb::k_tail<S, 16>, dim3(kTailCluster, 1, nf), dim3(mb::kTailThreads), sh.tail_smem[2], stream, pdl, kTailCluster, A)); launches++; }
     mark("k_tail");
@@ -1111,6 +1144,7 @@ int msckf_b200_create(const msckf_b200_config* cfg, msckf_b200_engine** out) {
   if (getenv("MSCKF_B200_NO_PDL")) b->use_pdl = false;
   if (getenv("MSCKF_B200_NO_DMMA")) b->gram_mma = false;
   if (getenv("MSCKF_B200_NO_FUSED_TAIL")) b->no_fused_tail = true;
+  if (const char* g = getenv("MSCKF_B200_TAIL_CHAINS")) { const int v = atoi(g); if (v == 1 || v == 2) b->tail_chains = v; }
   if (const char* g = getenv("MSCKF_B200_JAC_GROUP")) { const int v = atoi(g); if (v == 32 || v == 64 || v == 128) b->jac_group = v; }
   b->dtype = cfg->dtype; b->device = cfg->device; b->Mmax = cfg->max_clones; b->Tmax = cfg->max_tracks; b->Omax = cfg->max_obs;
   int rc = (cfg->dtype == MSCKF_B200_F32) ? static_cast<Engine<float>*>(b)->alloc() : static_cast<Engine<double>*>(b)->alloc();
@@ -1228,6 +1262,7 @@ int msckf_b200_get_covariance(msckf_b200_engine* e, void* out) { return e->impl-
 int msckf_b200_set_covariance(msckf_b200_engine* e, const void* in) { return e->impl->set_covariance(in); }
 int msckf_b200_get_counters(msckf_b200_engine* e, long long* counters) { return e->impl->get_counters(counters); }
 int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap) { return e->impl->last_dx(out, cap); }
+int msckf_b200_rank_pivots(msckf_b200_engine* e, double* out, int cap) { return e->impl->rank_pivots(out, cap); }
 int msckf_b200_kernel_times(msckf_b200_engine* e, float* ms, const char** names, int cap) { return e->impl->solo_ctx()->kernel_times(ms, names, cap); }
 int msckf_b200_tail_profile(msckf_b200_engine* e, unsigned long long* out, int cap) { return e->impl->tail_profile(out, cap); }
 int msckf_b200_set_option(msckf_b200_engine* e, int key, double value) {
@@ -1237,6 +1272,11 @@ int msckf_b200_set_option(msckf_b200_engine* e, int key, double value) {
   if (key == 3) { e->impl->no_fused_tail = value == 0; return 0; }
   if (key == 4) { e->impl->use_pdl = value != 0; return 0; }
   if (key == 5) { e->impl->gram_mma = value != 0; return 0; }
+  if (key == 7) {
+    if (value != 0 && value != 1 && value != 2) return fail(MSCKF_B200_ERR_ARG, "option 7: 0, 1 or 2");
+    e->impl->tail_chains = (int)value;
+    return 0;
+  }
   if (key == 6) {
     const int g = (int)value;
     if (g != 0 && g != 32 && g != 64 && g != 128) return fail(MSCKF_B200_ERR_ARG, "option 6: 0, 32, 64 or 128");

@@ -243,7 +243,10 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(const UpdArgs<S>* __restr
   cluster.sync();
   stamp();  // Gamma built
   if (crank == 0) {
-    for (int k = tid; k < n; k += kTailThreads) d0[k] = full ? (k < m ? 1.0 : 0.0) : G[(size_t)k * ld + k];
+    for (int k = tid; k < n; k += kTailThreads) {
+      d0[k] = full ? (k < m ? 1.0 : 0.0) : G[(size_t)k * ld + k];
+      if (crank == 0) ua.pivr[n + k] = d0[k];  // (diagnostics: the denominators of msckf_b200_rank_pivots)
+    }
     if (tid == 0) s_rank = 0;
   }
   __syncthreads();
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail(const UpdArgs<S>* __restr
           const double dk0 = d0[kb + k];
           const bool drop = !(dk0 > 0.0) || !(pg > thr * dk0) || rank_now >= rank_cap || !(pa > 0.0);
           if (!drop) rank_now++;
+          if (lane == 0) ua.pivr[kb + k] = pg;
           const double ig = drop ? 0.0 : rsqrt(pg), ia = drop ? 0.0 : rsqrt(pa);
           __syncwarp();
           if (lane > k && lane < nb) { DA[lane * LD + k] = sa * ia; if (!full) DG[lane * LD + k] = sg * ig; }

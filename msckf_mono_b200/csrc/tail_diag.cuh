@@ -19,6 +19,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef MSCKF_TF_PW
+#define MSCKF_TF_PW 8  // panel width of tf_factor_one (4 or 8; 8: four panels per block, 10.5 instead of 13.4 us per block)
+#endif
+
 namespace mb {
 
 constexpr int kFB = 32;        // block size of the fused form
@@ -40,7 +44,8 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
                                                double* __restrict__ LIA, double* __restrict__ idg, double* __restrict__ ida,
                                                const double* __restrict__ d0, int kb, int nb, double thr, int rank_cap, bool full,
                                                TfRank rk, int tid, int nthreads, double* __restrict__ TA /*[32][kFLD] scratch*/,
-                                               double* __restrict__ TG /*[32][kFLD] scratch*/, unsigned long long* dprof = nullptr) {
+                                               double* __restrict__ TG /*[32][kFLD] scratch*/, double* __restrict__ pivr,
+                                               unsigned long long* dprof = nullptr) {
   constexpr int LD = kFLD, PW = 4;
   int dpi = 0;
   auto dstamp = [&]() {
@@ -69,7 +74,7 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
     if (tid < 128) {
     // (1) the two 4 x 4 diagonal micro-blocks, redundantly in every thread of warps 0..3 (the row solvers of (2) need them
     // in registers; all eight warps doing it would make the half-rate FP64 pipe, not the pivot chain, the limit)
-    double Gm[PW][PW], Am[PW][PW], ivg[PW], iva[PW];
+    double Gm[PW][PW], Am[PW][PW], ivg[PW], iva[PW], pvs[PW];
 #pragma unroll
     for (int a = 0; a < PW; ++a)
 #pragma unroll
@@ -85,6 +90,7 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
       if (full) drop = (c0 + j >= nb) || !(dk0 > 0.0) || rk.a >= rank_cap;
       else drop = (c0 + j >= nb) || !(dk0 > 0.0) || !(pg > thr * dk0) || rk.g >= rank_cap;
       if (!drop) rk.g++;
+      pvs[j] = full ? 1.0 : pg;
       const double ig = (drop || full) ? 0.0 : tf_rsqrt_pos(pg);
       const bool dropa = drop || !(pa > 0.0);
       if (!dropa) rk.a++;
@@ -102,6 +108,10 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
 #pragma unroll
       for (int j = 0; j < PW; ++j) if (j == tid) { vg = ivg[j]; va = iva[j]; }
       idg[c0 + tid] = vg; ida[c0 + tid] = va;
+    }
+    if (tid == 127) {  // diagnostics (msckf_b200_rank_pivots): Gamma's pivots as they were compared -- plain stores, off the chain
+#pragma unroll
+      for (int j = 0; j < PW; ++j) if (c0 + j < nb) pivr[kb + c0 + j] = pvs[j];
     }
     // (2) one row of the panel per thread (rows c0 .. nb-1; warp 0: S'', warp 1: Gamma), solved in registers; a row inside the
     // micro-block reproduces the factor's own row (entries right of its diagonal are masked)
@@ -173,6 +183,175 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
   }
   dstamp();  // factors + inverses done
   // rows / columns of dropped or out-of-range pivots of the inverses are zero by construction (1 / L_kk := 0)
+  return rk;
+}
+
+// ---- the same factorisation for ONE matrix per CTA (k_tail_fused<S, 2>: Gamma's and S''s chains of diagonal blocks run on
+// two CTAs of the cluster, side by side).  S'' must follow Gamma's keep / drop decisions: the Gamma CTA publishes the flags of
+// a panel as ONE 32-bit word -- (block tag << 8) | drop bits -- with a plain DSMEM store into the S'' CTA's shared memory
+// (a single aligned word: no fence, nothing else to order).  The S'' CTA does not wait for it: it factorises its micro-block
+// assuming "nothing dropped" (its own non-positive pivots aside), then looks at the word, and only if Gamma did drop
+// something (the panel that meets the null space of H_o) repeats the micro-block with the real flags.  Gamma never waits.
+//   role 0: S'', following the flags   role 1: Gamma, deciding and publishing   role 2: S'' alone (m <= n: no Gamma)
+struct TfLink {
+  volatile unsigned* words;  // [32 / PW] role 0: local; role 1: the partner's (mapped) array
+};
+
+__device__ __noinline__ int tf_factor_one(double* __restrict__ D, double* __restrict__ LI, double* __restrict__ idv,
+                                          const double* __restrict__ d0, int kb, int nb, double thr, int rank_cap, int role, int rk,
+                                          int tid, int nthreads, unsigned tag /* > 0, grows with every block */, TfLink lk,
+                                          double* __restrict__ pivr, unsigned long long* dprof = nullptr) {
+  constexpr int LD = kFLD, PW = MSCKF_TF_PW, PH = PW / 2;
+  auto dstamp = [&](int slot) {  // fixed slots: 0 entry | 1 + 4 p + {0: micro + rows, 1: barrier, 2: trailing, 3: barrier} for panels p < 3 | 13 end
+    if (dprof && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); dprof[slot] = t_; }
+  };
+  dstamp(0);
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < kFB * LD; e += nthreads) LI[e] = (e / LD == e % LD) ? 1.0 : 0.0;  // the extra rows (see tf_factor_block)
+  __syncthreads();
+#pragma unroll 1
+  for (int c0 = 0; c0 < kFB; c0 += PW) {
+    if (c0 >= nb) {  // columns beyond the matrix: dropped indices (both CTAs skip them: nothing to publish)
+      if (tid < PW) idv[c0 + tid] = 0.0;
+      continue;
+    }
+    if (tid < 64) {
+      double Mm[PW][PW], iv[PW], pvs[PW];
+      unsigned bits = 0u;  // Gamma's drop flags of this panel (role 0: assumed clear on the first pass)
+      int rk1 = rk;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int a = 0; a < PW; ++a)
+#pragma unroll
+          for (int b = 0; b <= a; ++b) Mm[a][b] = D[(c0 + a) * LD + c0 + b];
+        rk1 = rk;
+        unsigned mine = 0u;
+#pragma unroll
+        for (int j = 0; j < PW; ++j) {
+          const double dk0 = d0[kb + c0 + j];
+          const double p = Mm[j][j];
+          bool drop;
+          if (role == 1) {
+            drop = (c0 + j >= nb) || !(dk0 > 0.0) || !(p > thr * dk0) || rk1 >= rank_cap;
+            if (drop) mine |= 1u << j;
+          } else if (role == 2) {
+            drop = (c0 + j >= nb) || !(dk0 > 0.0) || rk1 >= rank_cap || !(p > 0.0);
+          } else {
+            drop = ((bits >> j) & 1u) != 0u || !(p > 0.0);
+          }
+          if (!drop) rk1++;
+          pvs[j] = (role == 2) ? 1.0 : p;
+          const double i_ = drop ? 0.0 : tf_rsqrt_pos(p);
+          iv[j] = i_;
+#pragma unroll
+          for (int a = j + 1; a < PW; ++a) Mm[a][j] *= i_;
+#pragma unroll
+          for (int b = j + 1; b < PW; ++b)
+#pragma unroll
+            for (int a = b; a < PW; ++a) Mm[a][b] -= Mm[a][j] * Mm[b][j];
+        }
+        if (role == 1 && tid == 0) lk.words[c0 / PW] = (tag << 8) | mine;  // publish (one word, plain remote store)
+        if (role != 0 || pass == 1) break;
+        unsigned w = lk.words[c0 / PW];
+        for (int spin = 0; (w >> 8) != tag && spin < (1 << 22); ++spin) w = lk.words[c0 / PW];  // (bounded: a lost partner must not hang the device)
+        if ((w & 0xffu) == 0u) break;  // nothing dropped by Gamma: the speculative pass stands
+        bits = w & 0xffu;
+      }
+      rk = rk1;
+      if (tid < PW) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < PW; ++j) if (j == tid) v = iv[j];
+        idv[c0 + tid] = v;
+      }
+      if (role != 0 && tid == 63) {  // diagnostics (msckf_b200_rank_pivots): the pivots as they were compared -- plain stores
+#pragma unroll
+        for (int j = 0; j < PW; ++j) if (c0 + j < nb) pivr[kb + c0 + j] = pvs[j];
+      }
+      // one row per lane: warp 0 the panel rows c0 .. nb-1, warp 1 the extra rows 0 .. c0+3 (the inverse, transposed)
+      const int rrow = c0 + lane;
+      if (warp == 0 && rrow < nb) {
+        double x[PW];
+#pragma unroll
+        for (int j = 0; j < PW; ++j) x[j] = (c0 + j <= rrow) ? D[rrow * LD + c0 + j] : 0.0;
+#pragma unroll
+        for (int j = 0; j < PW; ++j) {
+          x[j] *= iv[j];
+          if (c0 + j > rrow) x[j] = 0.0;
+#pragma unroll
+          for (int jj = j + 1; jj < PW; ++jj) x[jj] -= x[j] * Mm[jj][j];
+        }
+#pragma unroll
+        for (int j = 0; j < PW; ++j) if (c0 + j <= rrow) D[rrow * LD + c0 + j] = x[j];
+      }
+      if (warp == 1 && lane < c0 + PW && lane < nb) {
+        double x[PW];
+#pragma unroll
+        for (int j = 0; j < PW; ++j) x[j] = LI[(c0 + j) * LD + lane];
+#pragma unroll
+        for (int j = 0; j < PW; ++j) {
+          x[j] *= iv[j];
+#pragma unroll
+          for (int jj = j + 1; jj < PW; ++jj) x[jj] -= x[j] * Mm[jj][j];
+        }
+#pragma unroll
+        for (int j = 0; j < PW; ++j) LI[(c0 + j) * LD + lane] = x[j];
+      }
+    }
+    if (c0 < 3 * PW) dstamp(1 + 4 * (c0 / PW));
+    __syncthreads();
+    if (c0 < 3 * PW) dstamp(2 + 4 * (c0 / PW));
+    // trailing update inside the block (rows / columns c0+4 .. nb-1, lower triangle) and of the extra rows; the 256 threads
+    // are split between the two: 128 as an 8 x 16 grid on the block, 128 on the extra rows
+    const int q0 = c0 + PW, nr = nb - q0;
+    if (nr > 0) {
+      const int h = tid >> 7, t7 = tid & 127, ty = t7 >> 4, tx = t7 & 15;
+      if (h == 0) {
+#pragma unroll 1
+        for (int i = q0 + ty; i < nb; i += 8) {
+          double2 av[PH];
+#pragma unroll
+          for (int u = 0; u < PH; ++u) av[u] = *reinterpret_cast<const double2*>(D + i * LD + c0 + 2 * u);
+#pragma unroll 1
+          for (int j = q0 + tx; j <= i; j += 16) {
+            double acc[PH];
+#pragma unroll
+            for (int u = 0; u < PH; ++u) {
+              const double2 bv = *reinterpret_cast<const double2*>(D + j * LD + c0 + 2 * u);
+              acc[u] = av[u].x * bv.x + av[u].y * bv.y;
+            }
+            double t = acc[0];
+#pragma unroll
+            for (int u = 1; u < PH; ++u) t += acc[u];
+            D[i * LD + j] -= t;
+          }
+        }
+      } else {
+        const int nact = min(q0, nb);
+#pragma unroll 1
+        for (int j = q0 + ty; j < nb; j += 8) {
+          double2 bv[PH];
+#pragma unroll
+          for (int u = 0; u < PH; ++u) bv[u] = *reinterpret_cast<const double2*>(D + j * LD + c0 + 2 * u);
+#pragma unroll 1
+          for (int i = tx; i < nact; i += 16) {
+            double acc[PH];
+#pragma unroll
+            for (int u = 0; u < PH; ++u) acc[u] = LI[(c0 + 2 * u) * LD + i] * bv[u].x + LI[(c0 + 2 * u + 1) * LD + i] * bv[u].y;
+            double t = acc[0];
+#pragma unroll
+            for (int u = 1; u < PH; ++u) t += acc[u];
+            LI[j * LD + i] -= t;
+          }
+        }
+      }
+    }
+    if (c0 < 3 * PW) dstamp(3 + 4 * (c0 / PW));
+    __syncthreads();
+    if (c0 < 3 * PW) dstamp(4 + 4 * (c0 / PW));
+  }
+  dstamp(13);
   return rk;
 }
 

@@ -59,7 +59,9 @@ __device__ __forceinline__ void tf_load_diag(double* D, const double* A, int ld,
   }
 }
 
-template <class S>
+// NCH = number of CTAs that run chains of diagonal blocks: 1 (cluster of 8: CTA 0 factorises Gamma's and S''s blocks together)
+// or 2 (cluster of 9: CTA 0 S'', CTA 1 Gamma, side by side -- tf_factor_one; the other seven CTAs are the workers either way).
+template <class S, int NCH>
 __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* __restrict__ args) {
   pdl_wait();
   pdl_launch();
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
   stamp();
   int wprof_i = 0;
   auto wstamp = [&]() {  // the same for the first worker CTA (slots 20..39)
-    if (prof && blockIdx.x == 1 && blockIdx.z == 0 && tid == 0 && wprof_i < 19) {
+    if (prof && (int)blockIdx.x == NCH && blockIdx.z == 0 && tid == 0 && wprof_i < 19) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) : : "memory");
       prof[20 + wprof_i++] = t;
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
   double* idg = d0 + ((n + 1) & ~1);         // [32] 1 / diag of the block's factor of G (0 = dropped)
   double* ida = idg + NB;                    // [32] same for A
   __shared__ int s_rankA, s_rankG;
+  __shared__ unsigned s_words[NB / 4];  // NCH = 2, CTA 0: Gamma's drop flags, one word per panel of the block (written by CTA 1)
   const int m = *m_in;
   const bool full = m <= n;  // all rows explicit and orthonormal: Gamma = I_m, nothing to decide, G untouched
   const int rank_cap = min(m, n);
@@ -132,8 +135,9 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
     return;
   }
   const int ncol = n + 1;
-  const int per = (ncol + C - 2) / (C - 1);  // RHS columns per CTA (<= 32); CTA 0 (the diagonal blocks) takes none
-  const int col0 = (crank - 1) * per, cw = (crank == 0) ? 0 : max(0, min(per, ncol - col0));
+  const int NWK = C - NCH, widx = crank - NCH;  // workers: the CTAs behind the chain CTAs
+  const int per = (ncol + NWK - 1) / NWK;    // RHS columns per worker (<= 32); the chain CTAs take none
+  const int col0 = widx * per, cw = (crank < NCH) ? 0 : max(0, min(per, ncol - col0));
   const int ncw4 = (cw + 3) / 4;
   // ---------------------------------------------------------------- Gamma = [[I_h, H_h], [H_h^T, Lambda]]: T'' already
   // holds H_h (rows < 15) and Lambda; only the lower triangle is read below, so patching the first 15 columns suffices
@@ -150,10 +154,14 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
     Ws[(size_t)c * ldt + k] = v;
   }
   for (int e = tid; e < NB * (ldt - n); e += kTailThreads) Ws[(size_t)(e / (ldt - n)) * ldt + n + e % (ldt - n)] = 0.0;
+  if (tid < NB / 4) s_words[tid] = 0u;
   cluster.sync();
   stamp();  // Gamma patched, right-hand sides staged
-  if (crank == 0) {
-    for (int k = tid; k < n; k += kTailThreads) d0[k] = full ? (k < m ? 1.0 : 0.0) : G[(size_t)k * ld + k];
+  if (crank < NCH) {
+    for (int k = tid; k < n; k += kTailThreads) {
+      d0[k] = full ? (k < m ? 1.0 : 0.0) : G[(size_t)k * ld + k];
+      if (crank == 0) ua.pivr[n + k] = d0[k];  // (diagnostics: the denominators of msckf_b200_rank_pivots)
+    }
     if (tid == 0) { s_rankA = 0; s_rankG = 0; }
   }
   __syncthreads();
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
     TfRank rk;
     rk.g = s_rankG; rk.a = s_rankA;
     __syncthreads();
-    rk = tf_factor_block(DG, DA, LIG, LIA, idg, ida, d0, kb, nb, thr, rank_cap, full, rk, tid, kTailThreads, WB, DT, stamps ? prof + 60 : nullptr);
+    rk = tf_factor_block(DG, DA, LIG, LIA, idg, ida, d0, kb, nb, thr, rank_cap, full, rk, tid, kTailThreads, WB, DT, ua.pivr, stamps ? prof + 60 : nullptr);
     if (tid == 0) { s_rankG = rk.g; s_rankA = rk.a; }
     if (stamps && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[77] = t_; }
     // the inverses go to the other CTAs through L2 (a DSMEM push of 2 x 8.7 KB to 7 CTAs runs at ~20 B/clk: 3 us)
@@ -177,12 +185,36 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
       if (!full) reinterpret_cast<double2*>(Lsc + NB * LD)[e] = reinterpret_cast<const double2*>(LIG)[e];
     }
   };
-  if (crank == 0) {
-    const int nb0 = min(NB, n);
-    if (!full) tf_load_diag(DG, G, ld, 0, nb0, tid);
-    tf_load_diag(DA, A, ld, 0, nb0, tid);
+  // NCH = 2: this chain CTA's own matrix lives in DA / LIA / ida whichever it is (CTA 0: S'', CTA 1: Gamma)
+  const bool chainG = (NCH == 2) && crank == 1;
+  double* __restrict__ Mch = chainG ? G : A;
+  TfLink link;
+  link.words = s_words;
+  if (NCH == 2 && chainG) link.words = cluster.map_shared_rank(s_words, 0);  // the Gamma CTA writes into CTA 0's array
+  auto factor_one = [&](int kb, int nb, bool stamps, double* Lsc) {
+    if (stamps && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[76] = t_; }
+    const int rk0 = chainG ? s_rankG : s_rankA;
     __syncthreads();
-    factor_block(0, nb0, prof != nullptr, Lsc_of(0));
+    const int role = full ? 2 : (chainG ? 1 : 0);
+    const int rk1 = tf_factor_one(DA, LIA, ida, d0, kb, nb, thr, rank_cap, role, rk0, tid, kTailThreads, (unsigned)(kb / NB) + 1u, link, ua.pivr, stamps ? prof + 60 : nullptr);
+    if (tid == 0) { if (chainG) s_rankG = rk1; else s_rankA = rk1; }
+    if (stamps && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[77] = t_; }
+    double* dst = Lsc + (chainG ? NB * LD : 0);
+    for (int e = tid; e < NB * LD / 2; e += kTailThreads) reinterpret_cast<double2*>(dst)[e] = reinterpret_cast<const double2*>(LIA)[e];
+  };
+  if (NCH == 1) {
+    if (crank == 0) {
+      const int nb0 = min(NB, n);
+      if (!full) tf_load_diag(DG, G, ld, 0, nb0, tid);
+      tf_load_diag(DA, A, ld, 0, nb0, tid);
+      __syncthreads();
+      factor_block(0, nb0, prof != nullptr, Lsc_of(0));
+    }
+  } else if (crank < NCH && !(chainG && full)) {
+    const int nb0 = min(NB, n);
+    tf_load_diag(DA, Mch, ld, 0, nb0, tid);
+    __syncthreads();
+    factor_one(0, nb0, prof != nullptr && crank == 0, Lsc_of(0));
   }
   stamp();  // diagonal block 0 done
   for (int kb = 0; kb < n; kb += NB) {
@@ -192,7 +224,73 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
     cluster.sync();  // B1: inverses of block kb in L2; trailing update of block kb - 1 complete
     const int blk = kb / NB;
     const double* Lsc = Lsc_of(blk);
-    if (crank == 0) {
+    if (NCH == 2 && crank < NCH) {
+      // ---- two chain CTAs (S'': 0, Gamma: 1), each ONE BLOCK AHEAD of the workers with its own matrix: the same steps as the
+      // single chain CTA below, for one matrix
+      if (nr <= 0) break;
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // B2 of this block
+      if (!(chainG && full)) {
+        const int nb2 = min(NB, nr);
+        constexpr int NS = NB * NB / kTailThreads;
+        constexpr int NLd = (NB * LD + kTailThreads - 1) / kTailThreads;
+        double sa_[NS], oa_[NLd];
+#pragma unroll
+        for (int u = 0; u < NS; ++u) {
+          const int e = tid + u * kTailThreads, l = e / NB, c = e % NB;
+          sa_[u] = (l < nb2 && c < nb) ? __ldcg(Mch + (size_t)(r0 + l) * ld + kb + c) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < NLd; ++u) {
+          const int e = tid + u * kTailThreads, i = e / LD, j = e % LD;
+          oa_[u] = (e < NB * LD && i < nb2 && j <= i) ? __ldcg(Mch + (size_t)(r0 + i) * ld + r0 + j) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < NS; ++u) {
+          const int e = tid + u * kTailThreads, l = e / NB, c = e % NB;
+          DA[l * LD + c] = sa_[u];
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int e = tid; e < NB * NB; e += kTailThreads) {  // X = rows * Linv^T
+          const int l = e / NB, j = e % NB;
+          double sa[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+          for (int c = 0; c < NB; c += 4) {
+            double a4[4], l4[4];
+            tf_ld4(DA + l * LD + c, a4); tf_ld4(LIA + j * LD + c, l4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sa[q] += a4[q] * l4[q];
+          }
+          WB[l * LD + j] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < NLd; ++u) {  // the next diagonal block = its leading tile of the trailing update
+          const int e = tid + u * kTailThreads, i = e / LD, j = e % LD;
+          if (e >= NB * LD) break;
+          double va = 0.0;
+          if (i < nb2 && j <= i) {
+            double sa[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+            for (int c = 0; c < NB; c += 4) {
+              double a4[4], b4[4];
+              tf_ld4(WB + i * LD + c, a4); tf_ld4(WB + j * LD + c, b4);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) sa[q] += a4[q] * b4[q];
+            }
+            va = oa_[u] - ((sa[0] + sa[1]) + (sa[2] + sa[3]));
+          }
+          DA[e] = va;
+        }
+        __syncthreads();
+        stamp();  // next diagonal block formed (CTA 0)
+        factor_one(r0, nb2, false, Lsc_of(blk + 1));
+        stamp();  // next diagonal block factorised (CTA 0)
+      }
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // B2
+      continue;
+    }
+    if (NCH == 1 && crank == 0) {
       // ---- CTA 0 runs the chain of diagonal blocks ONE BLOCK AHEAD of the other CTAs (round 2): while they solve the panel of
       // block kb, exchange it and run the trailing update, CTA 0 solves only the 32 panel rows of the NEXT diagonal block itself
       // (X = rows * Linv^T with the inverses it still holds), forms that block's leading tile and factorises it.  It has
@@ -284,8 +382,8 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
     // phase 2 (CTAs 1..7): the panel below the block, X = rows * Linv^T.  Rows are dealt to the CTAs in contiguous chunks (an
     // even number of rows each); lane = local row, warp w computes columns w, w + 8, w + 16, w + 24; the results go to a scratch
     // panel in L2 that every worker reads back after the barrier.  The W rows of this CTA are solved the same way (local).
-    const int chunk = (((nr + C - 2) / (C - 1)) + 1) & ~1;
-    const int i0 = (crank - 1) * chunk;
+    const int chunk = (((nr + NWK - 1) / NWK) + 1) & ~1;
+    const int i0 = widx * chunk;
     const int nloc = max(0, min(chunk, nr - i0));
     {
       {  // the inverses of block kb: all loads in flight before the first store
@@ -395,8 +493,8 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
       constexpr int kLead = (NB / 4) * (NB / 4 + 1) / 2;  // tiles of the leading 32 x 32 block: CTA 0's
       const int nrest = max(0, ntile - kLead);
       const int nitems = full ? nrest : 2 * nrest;
-      const int run = (nitems + C - 2) / (C - 1);
-      const int first = (crank - 1) * run;
+      const int run = (nitems + NWK - 1) / NWK;
+      const int first = widx * run;
       const int mine = max(0, min(run, nitems - first));
       const int nloc3 = mine + ncw4 * nt;
       for (int q = tid; q < nloc3; q += kTailThreads) {

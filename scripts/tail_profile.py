@@ -37,9 +37,10 @@ print("  deltas:", [round(b - a, 1) for a, b in zip(rel[:-1], rel[1:])])
 if ws:
     print("  worker CTA 1 (us since kernel start; per block: B1 passed, panel, B2 passed, exchanged, trailing):", [round((x - st[0]) / 1e3, 1) for x in ws])
 print("  block 0 factor (us):", round((int(buf[77]) - int(buf[76])) / 1e3, 2))
-dd = [int(x) for x in list(buf)[60:74] if x]
-if dd:
-    print("  block 0 fine stamps (us; entry, factors done, inverses done):", [round((x - dd[0]) / 1e3, 2) for x in dd])
+dd = [int(x) for x in list(buf)[60:74]]
+if dd[0]:
+    print("  block 0 fine stamps (us since entry; entry | per panel 0..2: micro-block + rows, barrier, trailing, barrier | end):",
+          [round((x - dd[0]) / 1e3, 2) if x else None for x in dd])
 sj = [int(x) for x in list(buf)[40:60] if x]
 if sj:
     rj = [round((x - sj[0]) / 1e3, 1) for x in sj]

@@ -158,6 +158,11 @@ int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap) {
   for (int i = 0; i < n && i < cap; ++i) out[i] = 0.0;
   return n;
 }
+int msckf_b200_rank_pivots(msckf_b200_engine* e, double* out, int cap) {
+  const int n = 15 + 6 * e->M;
+  for (int i = 0; i < n && i < cap; ++i) out[i] = 1.0;
+  return n;
+}
 int msckf_b200_set_option(msckf_b200_engine*, int, double) { return 0; }
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src) { *dst = *src; return 0; }
 long long msckf_b200_launch_count(const msckf_b200_engine* e) { return e->launches; }

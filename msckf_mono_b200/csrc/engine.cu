@@ -830,7 +830,14 @@ int Ctx<S>::stage(int mode, const msckf_b200_tracks* tracks, int threads) {
     Lmax[i] = lm;
     return 0;
   };
-  const int T = std::max(1, std::min(threads, nf));
+  // Staging threads: `threads` is an upper bound.  Measured on the 2 x 32-core host of the B200 box (scripts/e2e_breakdown.py):
+  // spreading the pack over 4 threads saves 13 us of 58 at 8 config-B filters (150 of 300 at 32) and then costs 100 (400) us
+  // more until the results are back -- the copy engine reads lines left dirty in several cores' caches -- so a batch
+  // only gets a second thread from 8 MB of observations on.
+  size_t in_bytes_est = 0;
+  for (int i = 0; i < nf; ++i)
+    if (tracks[i].n_tracks > 0 && tracks[i].obs_offset) in_bytes_est += (size_t)tracks[i].obs_offset[tracks[i].n_tracks] * (2 * sizeof(S) + sizeof(int));
+  const int T = std::max(1, std::min({threads, nf, 1 + (int)(in_bytes_est >> 23)}));
   auto for_all = [&](auto&& fn) -> int {
     if (T == 1) {
       for (int i = 0; i < nf; ++i) { const int r = fn(i); if (r != 0) return r; }

@@ -52,19 +52,34 @@ __global__ void __launch_bounds__(256) k_gram(const UpdArgs<S>* __restrict__ arg
   const bool diag = ta == tb;
   const int bc = threadIdx.x & 31, bg = threadIdx.x >> 5;
   double bz = 0.0;
-  for (int kb = k0; kb < k1; kb += GK) {
-    if (diag && threadIdx.x < GK) sU[threadIdx.x] = (kb + (int)threadIdx.x < k1) ? ur[kb + threadIdx.x] : 0.0;
-    for (int e = threadIdx.x; e < GK * GT; e += 256) {
-      const int kk = e / GT, cc = e % GT;
+  // operands of the next k-slab are fetched into registers while the current one is multiplied (the slabs are L2 hits of
+  // ~1 us latency; without the prefetch the kernel sat in long-scoreboard stalls: ncu, profiles/)
+  constexpr int NF = GK * GT / 256;
+  double fza[NF], fya[NF], fzb[NF], fyb[NF], fu = 0.0;
+  auto fetch = [&](int kb) {
+#pragma unroll
+    for (int u = 0; u < NF; ++u) {
+      const int e = threadIdx.x + 256 * u, kk = e / GT, cc = e % GT;
       const int k = kb + kk;
       const int ca = ta * GT + cc, cb = tb * GT + cc;
       const bool kin = k < k1;
-      sZa[kk][cc] = (kin && ca < c) ? Z[(size_t)k * c + ca] : 0.0;
-      sYa[kk][cc] = (kin && ca < c) ? Yq[(size_t)k * c + ca] : 0.0;
-      sZb[kk][cc] = (kin && cb < c) ? Z[(size_t)k * c + cb] : 0.0;
-      sYb[kk][cc] = (kin && cb < c) ? Yq[(size_t)k * c + cb] : 0.0;
+      fza[u] = (kin && ca < c) ? Z[(size_t)k * c + ca] : 0.0;
+      fya[u] = (kin && ca < c) ? Yq[(size_t)k * c + ca] : 0.0;
+      fzb[u] = diag ? fza[u] : ((kin && cb < c) ? Z[(size_t)k * c + cb] : 0.0);
+      fyb[u] = diag ? fya[u] : ((kin && cb < c) ? Yq[(size_t)k * c + cb] : 0.0);
+    }
+    if (diag && threadIdx.x < GK) fu = (kb + (int)threadIdx.x < k1) ? ur[kb + threadIdx.x] : 0.0;
+  };
+  fetch(k0);
+  for (int kb = k0; kb < k1; kb += GK) {
+    if (diag && threadIdx.x < GK) sU[threadIdx.x] = fu;
+#pragma unroll
+    for (int u = 0; u < NF; ++u) {
+      const int e = threadIdx.x + 256 * u, kk = e / GT, cc = e % GT;
+      sZa[kk][cc] = fza[u]; sYa[kk][cc] = fya[u]; sZb[kk][cc] = fzb[u]; sYb[kk][cc] = fyb[u];
     }
     __syncthreads();
+    if (kb + GK < k1) fetch(kb + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
       const double za0 = sZa[kk][ty], za1 = sZa[kk][ty + 16], ya0 = sYa[kk][ty], ya1 = sYa[kk][ty + 16];
@@ -136,19 +151,32 @@ __global__ void __launch_bounds__(128) k_gram_mma(const UpdArgs<S>* __restrict__
     for (int j = 0; j < 2; ++j) { c1[i][j][0] = c1[i][j][1] = 0.0; c2[i][j][0] = c2[i][j][1] = 0.0; }
   const bool diag = ta == tb;  // (see k_gram: this split's part of Z^T (U^T r); thread = (column, one of 4 k-groups))
   double bzs = 0.0;
-  for (int kb = k0; kb < k1; kb += GK) {
-    if (diag && tid < GK) sU[tid] = (kb + tid < k1) ? ur[kb + tid] : 0.0;
-    for (int e = tid; e < GK * GT; e += 128) {
-      const int kk = e / GT, cc = e % GT;
+  constexpr int NF = GK * GT / 128;  // register prefetch of the next k-slab (see k_gram)
+  double fza[NF], fya[NF], fzb[NF], fyb[NF], fu = 0.0;
+  auto fetch = [&](int kb) {
+#pragma unroll
+    for (int u = 0; u < NF; ++u) {
+      const int e = tid + 128 * u, kk = e / GT, cc = e % GT;
       const int k = kb + kk;
       const int ca = ta * GT + cc, cb = tb * GT + cc;
       const bool kin = k < k1;
-      sZa[kk][cc] = (kin && ca < c) ? Z[(size_t)k * c + ca] : 0.0;
-      sYa[kk][cc] = (kin && ca < c) ? Yq[(size_t)k * c + ca] : 0.0;
-      sZb[kk][cc] = (kin && cb < c) ? Z[(size_t)k * c + cb] : 0.0;
-      sYb[kk][cc] = (kin && cb < c) ? Yq[(size_t)k * c + cb] : 0.0;
+      fza[u] = (kin && ca < c) ? Z[(size_t)k * c + ca] : 0.0;
+      fya[u] = (kin && ca < c) ? Yq[(size_t)k * c + ca] : 0.0;
+      fzb[u] = diag ? fza[u] : ((kin && cb < c) ? Z[(size_t)k * c + cb] : 0.0);
+      fyb[u] = diag ? fya[u] : ((kin && cb < c) ? Yq[(size_t)k * c + cb] : 0.0);
+    }
+    if (diag && tid < GK) fu = (kb + tid < k1) ? ur[kb + tid] : 0.0;
+  };
+  fetch(k0);
+  for (int kb = k0; kb < k1; kb += GK) {
+    if (diag && tid < GK) sU[tid] = fu;
+#pragma unroll
+    for (int u = 0; u < NF; ++u) {
+      const int e = tid + 128 * u, kk = e / GT, cc = e % GT;
+      sZa[kk][cc] = fza[u]; sYa[kk][cc] = fya[u]; sZb[kk][cc] = fzb[u]; sYb[kk][cc] = fyb[u];
     }
     __syncthreads();
+    if (kb + GK < k1) fetch(kb + GK);
 #pragma unroll
     for (int ks = 0; ks < GK; ks += 4) {
       double az[2], ay[2], bz[2], by[2];

@@ -268,7 +268,7 @@ struct Ctx : CtxBase {
   int device = 0;
   bool owns_stream = false;
   cudaStream_t stream2 = nullptr;  // side branch of the update (k_blockdiag runs beside k_gram)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   int st_mode = -1;
   bool staged = false, timed_region = false;
   WorkerPool pool;
@@ -291,6 +291,7 @@ struct Ctx : CtxBase {
     CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_join2, cudaEventDisableTiming));
     return 0;
   }
   ~Ctx() override {
@@ -301,6 +302,7 @@ struct Ctx : CtxBase {
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_join2) cudaEventDestroy(ev_join2);
     if (ev_t0) cudaEventDestroy(ev_t0);
     if (ev_t1) cudaEventDestroy(ev_t1);
     if (stream2) cudaStreamDestroy(stream2);
@@ -1022,6 +1024,11 @@ int Ctx<S>::run_kernels(const LaunchShape& sh) {
     launches++;
     mark("k_blockdiag");
     if (fork) CK(cudaEventRecord(ev_join, stream2));
+    // the explicit head rows only need k_jac's outputs and own their part of T'', R'', r'': same side branch, joined before T''P
+    CK(launch_k(mb::k_rows<S>, dim3(sh.rows_gx, 1, nf), dim3(128), sh.rows_smem, sb, false, 1, A));
+    launches++;
+    mark("k_rows");
+    if (fork) CK(cudaEventRecord(ev_join2, stream2));
     if (sh.gram_mma & 2) { CK(launch_k(mb::k_gram_mma<S>, dim3(sh.gram_gx, sh.gram_gy, nf), dim3(128), 0, stream, false, 1, A)); if (sh.gram_mma & 1) launches++; }  // FP64 tensor cores (DMMA)
     if (sh.gram_mma & 1) CK(launch_k(mb::k_gram<S>, dim3(sh.gram_gx, sh.gram_gy, nf), dim3(256), 0, stream, false, 1, A));
     launches++;
@@ -1030,10 +1037,8 @@ int Ctx<S>::run_kernels(const LaunchShape& sh) {
     CK(launch_k(mb::k_assemble<S>, dim3(sh.asm_gx, 1, nf), dim3(256), 0, stream, false, 1, A));
     launches++;
     mark("k_assemble");
-    CK(launch_k(mb::k_rows<S>, dim3(sh.rows_gx, 1, nf), dim3(128), sh.rows_smem, stream, pdl, 1, A));
-    launches++;
-    mark("k_rows");
-    CK(launch_k(mb::k_gemm_tp<S>, dim3(sh.gemm_g, sh.gemm_g, nf), dim3(mb::kGemmThreads), 0, stream, pdl, 1, A));
+    if (fork) CK(cudaStreamWaitEvent(stream, ev_join2, 0));
+    CK(launch_k(mb::k_gemm_tp<S>, dim3(sh.gemm_g, sh.gemm_g, nf), dim3(mb::kGemmThreads), 0, stream, false, 1, A));
     mark("k_gemm_tp");
     CK(launch_k(mb::k_gemm_s<S>, dim3(sh.gemm_g, sh.gemm_g, nf), dim3(mb::kGemmThreads), 0, stream, pdl, 1, A));
     mark("k_gemm_s");

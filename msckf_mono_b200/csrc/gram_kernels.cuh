@@ -291,10 +291,15 @@ __device__ __forceinline__ void assemble_work(const UpdArgs<S>& A, int cta, int 
   double* __restrict__ R2 = A.R2;
   double* __restrict__ r2 = A.r2;
   const int c = n - kImuDim;
-  const bool full = *m_in <= n;  // m <= n: plain uncompressed update, all rows explicit (k_rows), no Gram part
+  const int m = *m_in;
+  const bool full = m <= n;  // m <= n: plain uncompressed update, all rows explicit (k_rows), no Gram part
+  // The explicit head rows belong to k_rows, which runs BESIDE this kernel (side branch of the graph): rows < hcap of T'', R''
+  // and r'', and -- when compressing -- columns < 15 of R'' (the coupling R_hH^T), are neither read nor written here.
+  const int hcap = full ? m : kImuDim, ccap = full ? 0 : kImuDim;
   const size_t total = (size_t)n * n;
   for (size_t e = (size_t)cta * 256 + threadIdx.x; e < total; e += (size_t)ncta * 256) {
     const int a = (int)(e / n), b = (int)(e % n);
+    if (a < hcap) continue;
     double tv = 0.0, rv = 0.0;
     if (!full && a >= kImuDim && b >= kImuDim) {
       const int ac = a - kImuDim, bc = b - kImuDim;
@@ -309,11 +314,12 @@ __device__ __forceinline__ void assemble_work(const UpdArgs<S>& A, int cta, int 
       rv = d2 - g2;
     }
     T2[(size_t)a * ld + b] = tv;
-    R2[(size_t)a * ld + b] = rv;
+    if (b >= ccap) R2[(size_t)a * ld + b] = rv;
   }
   // beta = blk(sum X^T r) - Z^T (U^T r); the second term arrives as split-K partials from the Gram kernel's diagonal tiles
   const double* __restrict__ bzp = A.bzp;
   for (int a = cta * 256 + threadIdx.x; a < n; a += ncta * 256) {
+    if (a < hcap) continue;
     double v = 0.0;
     if (!full && a >= kImuDim) {
       const int ac = a - kImuDim;
@@ -386,6 +392,14 @@ __device__ __forceinline__ void rows_work(const UpdArgs<S>& A, int j, double* __
   double* V = sh;
   double* W = sh + 3 * L2;
   for (int e = tid; e < 3 * L2; e += nthr) V[e] = (double)Vg[3 * 2 * (size_t)o0 + e];
+  // this feature owns rows h0 .. h0+nh-1 of T'', R'' (and, when compressing, the same columns of R'' below row 15): clear them,
+  // then fill in what is not zero -- k_assemble leaves them alone, so the two kernels run side by side
+  for (int e = tid; e < nh * n; e += nthr) {
+    const int t = e / n, b = e % n;
+    T2[(size_t)(h0 + t) * ld + b] = 0.0;
+    R2[(size_t)(h0 + t) * ld + b] = 0.0;
+    if (!full && b >= kImuDim) R2[(size_t)b * ld + (h0 + t)] = 0.0;
+  }
   __syncthreads();
   if (tid < 6) {  // v_k^T v_l : (0,0) (1,1) (2,2) (0,1) (0,2) (1,2)
     const int ka[6] = {0, 1, 2, 0, 0, 1}, kb[6] = {0, 1, 2, 1, 2, 2};

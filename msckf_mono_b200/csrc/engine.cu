@@ -267,7 +267,7 @@ struct Ctx : CtxBase {
   size_t in_used = 0, rep_used = 0;
   int device = 0;
   bool owns_stream = false;
-  cudaStream_t stream2 = nullptr;  // side branch of the update (k_blockdiag runs beside k_gram)
+  cudaStream_t stream2 = nullptr, stream3 = nullptr;  // side branches of the update (k_blockdiag, k_rows run beside k_gram)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   int st_mode = -1;
   bool staged = false, timed_region = false;
@@ -289,6 +289,7 @@ struct Ctx : CtxBase {
     CK(cudaSetDevice(device));
     CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&stream3, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_join2, cudaEventDisableTiming));
@@ -306,6 +307,7 @@ struct Ctx : CtxBase {
     if (ev_t0) cudaEventDestroy(ev_t0);
     if (ev_t1) cudaEventDestroy(ev_t1);
     if (stream2) cudaStreamDestroy(stream2);
+    if (stream3) cudaStreamDestroy(stream3);
     if (owns_stream && stream) cudaStreamDestroy(stream);
   }
   void drop_graphs() {
@@ -1018,17 +1020,17 @@ int Ctx<S>::run_kernels(const LaunchShape& sh) {
     mark("k_jac");
     // k_blockdiag and k_gram both depend on k_jac only: two branches (a fork / join in the captured graph)
     const bool fork = !profile();  // per-kernel event timing keeps everything on one stream
-    cudaStream_t sb = fork ? stream2 : stream;
-    if (fork) { CK(cudaEventRecord(ev_fork, stream)); CK(cudaStreamWaitEvent(stream2, ev_fork, 0)); }
+    cudaStream_t sb = fork ? stream2 : stream, sr = fork ? stream3 : stream;
+    if (fork) { CK(cudaEventRecord(ev_fork, stream)); CK(cudaStreamWaitEvent(stream2, ev_fork, 0)); CK(cudaStreamWaitEvent(stream3, ev_fork, 0)); }
     CK(launch_k(mb::k_blockdiag<S>, dim3(sh.bd_gx, 1, nf), dim3(128), 0, sb, false, 1, A));
     launches++;
     mark("k_blockdiag");
     if (fork) CK(cudaEventRecord(ev_join, stream2));
-    // the explicit head rows only need k_jac's outputs and own their part of T'', R'', r'': same side branch, joined before T''P
-    CK(launch_k(mb::k_rows<S>, dim3(sh.rows_gx, 1, nf), dim3(128), sh.rows_smem, sb, false, 1, A));
+    // the explicit head rows only need k_jac's outputs and own their part of T'', R'', r'': a branch of their own, joined before T''P
+    CK(launch_k(mb::k_rows<S>, dim3(sh.rows_gx, 1, nf), dim3(128), sh.rows_smem, sr, false, 1, A));
     launches++;
     mark("k_rows");
-    if (fork) CK(cudaEventRecord(ev_join2, stream2));
+    if (fork) CK(cudaEventRecord(ev_join2, stream3));
     if (sh.gram_mma & 2) { CK(launch_k(mb::k_gram_mma<S>, dim3(sh.gram_gx, sh.gram_gy, nf), dim3(128), 0, stream, false, 1, A)); if (sh.gram_mma & 1) launches++; }  // FP64 tensor cores (DMMA)
     if (sh.gram_mma & 1) CK(launch_k(mb::k_gram<S>, dim3(sh.gram_gx, sh.gram_gy, nf), dim3(256), 0, stream, false, 1, A));
     launches++;

@@ -147,15 +147,20 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
       G[(size_t)a * ld + b] = (a < kImuDim) ? ((a == b) ? 1.0 : 0.0) : G[(size_t)b * ld + a];
     }
   }
-  for (int e = tid; e < NB * n; e += kTailThreads) {  // consecutive threads -> consecutive k: conflict-free stores
-    const int c = e / n, k = e % n, col = col0 + c;
-    double v = 0.0;
-    if (c < cw) v = (col < n) ? TP[(size_t)k * ld + col] : r2[k];
-    Ws[(size_t)c * ldt + k] = v;
-  }
-  for (int e = tid; e < NB * (ldt - n); e += kTailThreads) Ws[(size_t)(e / (ldt - n)) * ldt + n + e % (ldt - n)] = 0.0;
   if (tid < NB / 4) s_words[tid] = 0u;
-  cluster.sync();
+  // split barrier: the chain CTAs only wait for everybody's part of the Gamma patch, not for the workers' staging of the
+  // right-hand sides (7 us of strided loads that nobody needs before the first panel)
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  if (crank >= NCH) {
+    for (int e = tid; e < NB * n; e += kTailThreads) {  // consecutive threads -> consecutive k: conflict-free stores
+      const int c = e / n, k = e % n, col = col0 + c;
+      double v = 0.0;
+      if (c < cw) v = (col < n) ? TP[(size_t)k * ld + col] : r2[k];
+      Ws[(size_t)c * ldt + k] = v;
+    }
+    for (int e = tid; e < NB * (ldt - n); e += kTailThreads) Ws[(size_t)(e / (ldt - n)) * ldt + n + e % (ldt - n)] = 0.0;
+  }
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   stamp();  // Gamma patched, right-hand sides staged
   if (crank < NCH) {
     for (int k = tid; k < n; k += kTailThreads) {

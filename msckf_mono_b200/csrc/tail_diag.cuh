@@ -188,8 +188,8 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
 
 // ---- the same factorisation for ONE matrix per CTA (k_tail_fused<S, 2>: Gamma's and S''s chains of diagonal blocks run on
 // two CTAs of the cluster, side by side).  S'' must follow Gamma's keep / drop decisions: the Gamma CTA publishes the flags of
-// a panel as ONE 32-bit word -- (block tag << 8) | drop bits -- with a plain DSMEM store into the S'' CTA's shared memory
-// (a single aligned word: no fence, nothing else to order).  The S'' CTA does not wait for it: it factorises its micro-block
+// a panel as ONE 32-bit word -- (block tag << 8) | drop bits -- with an atomic exchange into the S'' CTA's shared memory
+// through DSMEM (a single word: no fence, nothing else to order).  The S'' CTA does not wait for it: it factorises its micro-block
 // assuming "nothing dropped" (its own non-positive pivots aside), then looks at the word, and only if Gamma did drop
 // something (the panel that meets the null space of H_o) repeats the micro-block with the real flags.  Gamma never waits.
 //   role 0: S'', following the flags   role 1: Gamma, deciding and publishing   role 2: S'' alone (m <= n: no Gamma)
@@ -251,10 +251,17 @@ __device__ __noinline__ int tf_factor_one(double* __restrict__ D, double* __rest
 #pragma unroll
             for (int a = b; a < PW; ++a) Mm[a][b] -= Mm[a][j] * Mm[b][j];
         }
-        if (role == 1 && tid == 0) lk.words[c0 / PW] = (tag << 8) | mine;  // publish (one word, plain remote store)
+        // publish / poll the panel's word with atomics (one word is the whole message; atomics keep the exchange well-defined
+        // for the memory model and for racecheck); one lane per warp polls, the warp gets the word by shuffle
+        if (role == 1 && tid == 0) atomicExch(const_cast<unsigned*>(lk.words) + c0 / PW, (tag << 8) | mine);
         if (role != 0 || pass == 1) break;
-        unsigned w = lk.words[c0 / PW];
-        for (int spin = 0; (w >> 8) != tag && spin < (1 << 22); ++spin) w = lk.words[c0 / PW];  // (bounded: a lost partner must not hang the device)
+        unsigned w = 0u;
+        if (lane == 0) {
+          unsigned* wp = const_cast<unsigned*>(lk.words) + c0 / PW;
+          w = atomicOr(wp, 0u);
+          for (int spin = 0; (w >> 8) != tag && spin < (1 << 22); ++spin) w = atomicOr(wp, 0u);  // (bounded: a lost partner must not hang the device)
+        }
+        w = __shfl_sync(0xffffffffu, w, 0);
         if ((w & 0xffu) == 0u) break;  // nothing dropped by Gamma: the speculative pass stands
         bits = w & 0xffu;
       }

@@ -161,7 +161,9 @@ int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap);
  * compared with the rank threshold (option 0).  Directions in the null space of H_o show up as rounding noise here; the gap
  * between that noise and the smallest kept pivot is the margin of the decision.  Returns 15 + 6 M. */
 int msckf_b200_rank_pivots(msckf_b200_engine* e, double* out, int cap);
-/* option keys: 0 = rank threshold of the compression (relative pivot of the basis Gram matrix = squared sine to the span of the previous basis vectors, default 1e-11);
+/* option keys: 0 = rank threshold of the compression (relative pivot of the basis Gram matrix = squared sine to the span of the previous basis vectors, default 1e-9:
+ *                  measured pivots of null directions are rounding noise up to ~2e-11, the smallest real pivot of the test windows is > 1e-3,
+ *                  see msckf_b200_rank_pivots);
  *              1 = record per-kernel CUDA events in _launch (profiling aid, default off);
  *              2 = replay the update's kernel sequence as a CUDA graph when the batch signature repeats (default on);
  *              3 = fuse the forward substitution into the blocked Cholesky of the tail kernel where the window allows it
@@ -171,7 +173,10 @@ int msckf_b200_rank_pivots(msckf_b200_engine* e, double* out, int cap);
  *                  0 = SIMT DFMA tiles -- same results to fp64 rounding);
  *              6 = threads that work on one track in the feature kernel: 128 (a CTA per track: lowest latency), 64, or 32
  *                  (a warp per track, two tracks per CTA: highest throughput); 0 = by batch size (default: 128 for one
- *                  filter, 32 for a device batch).  The results are bit-identical for every value. */
+ *                  filter, 32 for a device batch).  The results are bit-identical for every value;
+ *              7 = CTAs that run the tail's chains of diagonal blocks: 2 (default where the device accepts clusters of 9: Gamma's
+ *                  and S''s chains side by side on two CTAs, seven worker CTAs) or 1 (cluster of 8, both chains on one CTA);
+ *                  0 = default.  Same rank decisions; results agree to fp64 rounding. */
 int msckf_b200_set_option(msckf_b200_engine* e, int key, double value);
 /* checkpoint / resume: copy the complete filter state of src into dst (same dtype and capacities) */
 int msckf_b200_copy_state(msckf_b200_engine* dst, const msckf_b200_engine* src);

@@ -123,8 +123,10 @@ int msckf_b200_update(msckf_b200_engine* e, int mode, const msckf_b200_tracks* t
 typedef struct msckf_b200_batch msckf_b200_batch;
 int msckf_b200_batch_create(msckf_b200_engine** engines, int n, msckf_b200_batch** out);
 int msckf_b200_batch_destroy(msckf_b200_batch* b);
-/* tracks[n] / reports[n]: one per engine, in the order given to _create; reports may be NULL.  `threads` host threads share
- * the validation and packing of the n track batches (<= 1: the calling thread does all of it). */
+/* tracks[n] / reports[n]: one per engine, in the order given to _create; reports may be NULL.  Up to `threads` host threads
+ * share the validation and packing of the n track batches (<= 1: the calling thread does all of it); the engine uses fewer
+ * for small batches -- one per 8 MB of observations: packing from several cores makes the following host-to-device copy slower
+ * than the packing gets faster (measured, profiles/README.md). */
 int msckf_b200_batch_update_async(msckf_b200_batch* b, int mode, const msckf_b200_tracks* tracks, int threads);
 int msckf_b200_batch_fetch(msckf_b200_batch* b, msckf_b200_report* reports);
 int msckf_b200_batch_update(msckf_b200_batch* b, int mode, const msckf_b200_tracks* tracks, msckf_b200_report* reports, int threads);

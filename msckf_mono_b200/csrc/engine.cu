@@ -370,9 +370,10 @@ struct Engine : EngineBase {
   void drop_graphs() override { solo.drop_graphs(); if (group) static_cast<Ctx<S>*>(group)->drop_graphs(); }
 
   static int& tail9_clusters() { static int v = 0; return v; }  // co-resident clusters of 9 (0: not available)
-  static int set_func_attrs() {
-    static bool done = false;  // (per scalar type; the attribute is per function and device-wide)
-    if (done) return 0;
+  static int set_func_attrs(int dev) {
+    static bool done[64] = {};  // (per scalar type and device: function attributes belong to the device's context)
+    if (dev < 0 || dev >= 64) return fail(MSCKF_B200_ERR_ARG, "device index");
+    if (done[dev]) return 0;
     CK(cudaFuncSetAttribute(mb::k_tri<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_jac<S, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_jac<S, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
@@ -393,7 +394,7 @@ struct Engine : EngineBase {
     cudaGetLastError();
     CK(cudaFuncSetAttribute(mb::k_tail<S, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     CK(cudaFuncSetAttribute(mb::k_tail<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    done = true;
+    done[dev] = true;
     return 0;
   }
 
@@ -474,7 +475,7 @@ struct Engine : EngineBase {
     RC(solo.rep.ensure(up256(Plan<S>::rep_bytes(Tmax)), nullptr));
     CK(cudaMallocHost(&h_st, sizeof(mb::DevState<S>)));
     memset(h_st, 0, sizeof(mb::DevState<S>));
-    RC(set_func_attrs());
+    RC(set_func_attrs(device));
     CK(cudaStreamSynchronize(stream));
     return 0;
   }

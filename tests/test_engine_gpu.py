@@ -210,6 +210,33 @@ def test_track_group_sizes_of_the_feature_kernel_are_bit_identical(dtype):
             assert np.array_equal(a, b)
 
 
+def test_tail_with_one_and_two_chain_ctas_agree_and_rank_pivots_show_the_gap():
+    """engine option 7: the tail's chains of diagonal blocks on two CTAs of a 9-CTA cluster (default where the device accepts
+    that cluster size) or on one CTA of an 8-CTA cluster (the fallback): same rank, same flags, results equal to rounding.
+    `msckf_b200_rank_pivots` shows what the rank decision saw: n - rank pivots at rounding-noise level, far below the
+    threshold, and every kept pivot far above it."""
+    from msckf_mono_b200 import capi
+    wl = synth.make_window_workload(n_features=300, n_clones=30, seq=0)
+    out = []
+    for chains in (2, 1):
+        f = make_engine(np.float64, max_clones=40, max_tracks=512, max_obs=512 * 30)
+        synth.drive(f, wl, marginalize_last=False)
+        e = capi.Engine(np.float64, borrowed=f.engineHandle())
+        e.set_option(7, float(chains))
+        f.marginalize()
+        pv = e.rank_pivots()
+        out.append((f.getCovariance(), f.lastReport()["accepted"].copy(), f.counters()["rows_kept"], pv))
+    (Pa, acca, ra, pva), (Pb, accb, rb, pvb) = out
+    assert ra == rb and np.array_equal(acca, accb)
+    assert np.max(np.abs(Pa - Pb)) <= 1e-7 * np.max(np.abs(Pa))
+    for pv, r in ((pva, ra), (pvb, rb)):
+        n = pv.size
+        assert n == 15 + 6 * 30
+        dropped = np.sort(pv)[: n - r]
+        kept = np.sort(pv)[n - r:]
+        assert np.all(np.abs(dropped) < 1e-10) and np.all(kept > 1e-6), (dropped, kept[:3])
+
+
 def test_batched_entry_point_matches_individual_updates():
     """`msckf_mono_marginalize_batch` (host work on several threads, one stream per filter) gives bit-identical filters to
     calling marginalize() one by one."""

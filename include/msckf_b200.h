@@ -161,7 +161,7 @@ int msckf_b200_last_delta_x(msckf_b200_engine* e, double* out, int cap);
 /* diagnostics of the last update's rank decision: for every index of the compressed system, the pivot of the basis Gram matrix
  * relative to its original diagonal (the squared sine against the span of the previous basis vectors) at the moment it was
  * compared with the rank threshold (option 0).  Directions in the null space of H_o show up as rounding noise here; the gap
- * between that noise and the smallest kept pivot is the margin of the decision.  Returns 15 + 6 M. */
+ * between that noise and the smallest kept pivot is the margin of the decision.  Returns the dimension 15 + 6 M of that update (0 before the first one). */
 int msckf_b200_rank_pivots(msckf_b200_engine* e, double* out, int cap);
 /* option keys: 0 = rank threshold of the compression (relative pivot of the basis Gram matrix = squared sine to the span of the previous basis vectors, default 1e-9:
  *                  measured pivots of null directions are rounding noise up to ~2e-11, the smallest real pivot of the test windows is > 1e-3,

@@ -363,6 +363,7 @@ struct Engine : EngineBase {
          *d_y = nullptr, *d_dx = nullptr, *d_idiag = nullptr, *d_pivr = nullptr;
   mb::DevState<S>* h_st = nullptr;
   int nmax = 0, ldp = 0, ld = 0;
+  mutable int pivr_n = 0;  // dimension of the last update that made a rank decision (msckf_b200_rank_pivots)
   bool initialized = false;
   Ctx<S> solo;
 
@@ -597,6 +598,7 @@ struct Engine : EngineBase {
   void fill_args(mb::UpdArgs<S>& a, const Plan<S>& p, int mode) const {
     memset(&a, 0, sizeof(a));
     a.n_tracks = p.N; a.M = M; a.Lmax = p.Lmax; a.ldp = ldp; a.ld = ld; a.n = 15 + 6 * M; a.mode = mode;
+    if (p.N > 0 && mode != MSCKF_B200_TRIANGULATE) pivr_n = a.n;  // (the window may shrink before msckf_b200_rank_pivots is asked)
     a.K = 3 * p.N;
     int nsplit = std::max(1, std::min(kMaxSplit, a.K / 96));
     int kchunk = (a.K + nsplit - 1) / nsplit;
@@ -710,7 +712,8 @@ struct Engine : EngineBase {
 
   int rank_pivots(double* out, int cap) override {
     CK(cudaSetDevice(device));
-    const int n = 15 + 6 * M;
+    const int n = pivr_n;  // dimension of the last update (0: none yet)
+    if (n <= 0) return 0;
     std::vector<double> tmp(2 * (size_t)n);
     CK(cudaMemcpyAsync(tmp.data(), d_pivr, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));

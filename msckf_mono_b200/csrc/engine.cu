@@ -1113,7 +1113,7 @@ int Ctx<S>::fetch(msckf_b200_report* reports) {
       rep->rank = p.h_mr[1];
     }
   }
-  if (status != 0) return fail(status, "non-finite delta-x or covariance after the update (the update has been applied, like msckf.h:1369-1418 would)");
+  if (status != 0) return fail(status, "non-finite delta-x or covariance after the update (the update has been applied, like msckf.h:1369-1418 would), or the tail kernel's two chain CTAs lost their hand-off");
   return 0;
 }
 }  // namespace

@@ -195,6 +195,7 @@ __device__ __noinline__ TfRank tf_factor_block(double* __restrict__ DG, double* 
 //   role 0: S'', following the flags   role 1: Gamma, deciding and publishing   role 2: S'' alone (m <= n: no Gamma)
 struct TfLink {
   volatile unsigned* words;  // [32 / PW] role 0: local; role 1: the partner's (mapped) array
+  int* timed_out;            // role 0: set when the partner's word never arrived (reported as a failed update, never silent)
 };
 
 __device__ __noinline__ int tf_factor_one(double* __restrict__ D, double* __restrict__ LI, double* __restrict__ idv,
@@ -262,6 +263,7 @@ __device__ __noinline__ int tf_factor_one(double* __restrict__ D, double* __rest
           for (int spin = 0; (w >> 8) != tag && spin < (1 << 22); ++spin) w = atomicOr(wp, 0u);  // (bounded: a lost partner must not hang the device)
         }
         w = __shfl_sync(0xffffffffu, w, 0);
+        if ((w >> 8) != tag) { if (tid == 0) *lk.timed_out = 1; w = 0xffu; }  // lost partner: drop the panel and flag the update
         if ((w & 0xffu) == 0u) break;  // nothing dropped by Gamma: the speculative pass stands
         bits = w & 0xffu;
       }

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
   double* idg = d0 + ((n + 1) & ~1);         // [32] 1 / diag of the block's factor of G (0 = dropped)
   double* ida = idg + NB;                    // [32] same for A
   __shared__ int s_rankA, s_rankG;
+  __shared__ int s_timeout;             // NCH = 2, CTA 0: the Gamma CTA's flags did not arrive within the polling bound
   __shared__ unsigned s_words[NB / 4];  // NCH = 2, CTA 0: Gamma's drop flags, one word per panel of the block (written by CTA 1)
   const int m = *m_in;
   const bool full = m <= n;  // all rows explicit and orthonormal: Gamma = I_m, nothing to decide, G untouched
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
     }
   }
   if (tid < NB / 4) s_words[tid] = 0u;
+  if (tid == 0) s_timeout = 0;
   // split barrier: the chain CTAs only wait for everybody's part of the Gamma patch, not for the workers' staging of the
   // right-hand sides (7 us of strided loads that nobody needs before the first panel)
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
   double* __restrict__ Mch = chainG ? G : A;
   TfLink link;
   link.words = s_words;
+  link.timed_out = &s_timeout;
   if (NCH == 2 && chainG) link.words = cluster.map_shared_rank(s_words, 0);  // the Gamma CTA writes into CTA 0's array
   auto factor_one = [&](int kb, int nb, bool stamps, double* Lsc) {
     if (stamps && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_) : : "memory"); prof[76] = t_; }
@@ -544,7 +547,10 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_fused(const UpdArgs<S>* _
     wstamp();  // trailing update + W tiles done
   }
   cluster.sync();
-  if (gtid == 0) *rank_out = s_rankA;
+  if (gtid == 0) {
+    *rank_out = s_rankA;
+    if (NCH == 2 && s_timeout) ua.m_out[2] = 1;  // reported by msckf_b200_fetch as MSCKF_B200_ERR_NUMERIC
+  }
   for (int e = tid; e < n * cw; e += kTailThreads) {
     const int row = e / cw, cc = e % cw, col = col0 + cc;
     const double v = Ws[(size_t)cc * ldt + row];

@@ -13,12 +13,14 @@ __global__ void __cluster_dims__(2, 1, 1) k_check(const double* Ain, const doubl
   __shared__ __align__(16) double D[kFB * kFLD], LI[kFB * kFLD];
   __shared__ double idv[kFB], d0[kFB + 2];
   __shared__ unsigned s_words[kFB / 4];
+  __shared__ int s_timeout;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = cluster.block_rank(), tid = threadIdx.x;
   if (tid < kFB / 4) s_words[tid] = 0u;
   cluster.sync();
   TfLink lk;
   lk.words = s_words;
+  lk.timed_out = &s_timeout;
   if (crank == 1) lk.words = cluster.map_shared_rank(s_words, 0);
   int rk = 0;
   for (int rep = 0; rep < reps; ++rep) {

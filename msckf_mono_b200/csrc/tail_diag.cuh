@@ -2,20 +2,20 @@
 //
 // Round 1 factorised a diagonal block with one warp per matrix, a shuffle + shared-memory round trip per pivot and a second
 // pair of warps building the inverses one pivot behind (the S'' warp polling Gamma's keep / drop decision through a
-// volatile flag): ~540 ns per pivot, 17 us per block, half of the kernel.  Two measurements shaped this version
-// (%globaltimer stamps inside the function, profiles/r02_*):
-//   * per-pivot communication is what costs: here the block is itself blocked by panels of 4 columns, the two 4 x 4
-//     diagonal micro-blocks (Gamma's and S''s) are factorised REDUNDANTLY in registers by every thread of the two warps that
-//     need them -- static indices, right-looking, so the dependent chain of a pivot is rsqrt -> multiply -> one FMA -- and
-//     the keep / drop decision of each pivot (Gamma's pivot against thr x its original diagonal, the rank cap; S'' follows)
-//     is evaluated by every thread from the same numbers: nobody waits for a flag, and the only synchronisation is two CTA
-//     barriers per panel;
-//   * code that runs once per call is bound by instruction fetch (~5-7 cycles per instruction from L2 once the body exceeds
-//     the 32 KB L1.5 instruction cache; a first version with 8 x 8 micro-blocks and a fully unrolled 32-step inverse was
-//     3 157 instructions and took 21 us per block): every loop here is rolled except the 4 x 4 micro-block itself.
-// After the eight panels the inverses of the two factors are built block row by block row (8 x 8 blocks):
-// Linv_ij = -Linv_ii (sum_k L_ik Linv_kj), two short dot products per element, all threads.  Only the inverses leave the
-// block -- the panels below it are X = rows x Linv^T -- so the factor of the diagonal block is never exported.
+// volatile flag): ~540 ns per pivot, 17 us per block, half of the kernel.  Measurements that shaped this version
+// (%globaltimer stamps inside the functions, profiles/r02_tail_stamps.md):
+//   * per-pivot communication is what costs: the block is itself blocked by panels, the diagonal micro-block of a panel is
+//     factorised REDUNDANTLY in registers by every thread of the warps that need it -- static indices, right-looking, so the
+//     dependent chain of a pivot is rsqrt -> multiply -> one FMA (80 cycles, scripts/fp64_latency.cu) -- and the keep / drop
+//     decision of each pivot (Gamma's pivot against thr x its original diagonal, the rank cap; S'' follows) is evaluated by
+//     every thread from the same numbers; two CTA barriers per panel;
+//   * code that runs once per call is bound by instruction fetch (~5-7 cycles per instruction once the body exceeds the
+//     L1.5 instruction cache; a first version with a fully unrolled 32-step inverse was 3 157 instructions and took 21 us per
+//     block): every loop here is rolled except the micro-block itself;
+//   * the inverses of the factors ride along the panels as 32 extra rows (rows of the identity, solved like panel rows):
+//     no separate inverse stage.  Only the inverses leave the block -- the panels below it are X = rows x Linv^T.
+// Two entry points: tf_factor_block (Gamma and S'' together on one CTA, 4-column panels: the 8-CTA cluster form) and
+// tf_factor_one (one matrix per CTA, 8-column panels, Gamma's flags handed to the S'' CTA through DSMEM: the 9-CTA form).
 #pragma once
 #include "common.cuh"
 

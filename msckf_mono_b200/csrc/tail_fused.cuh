@@ -1,26 +1,32 @@
 // msckf_mono_b200/csrc/tail_fused.cuh
-// The serial part of the EKF tail for windows up to ~35 clones as ONE thread-block-cluster kernel (8 CTAs, 8 SMs of a GPC):
+// The serial part of the EKF tail for windows up to 34 clones as ONE thread-block-cluster kernel:
 //     Gamma (Gram matrix of the basis)  -> rank decision      }  rank-revealing Cholesky of Gamma (G) and S'' (A),
 //     S'' = L L^T over the kept indices                        }  blocked by 32, A following G's decisions
-//     W = L^-1 [T''P | r'']   fused into the factorisation: every CTA keeps its share of the right-hand-side columns as
-//                             rows in shared memory and treats them as extra panel rows
-// followed by  P <- P - W^T W (k_syrk, all SMs) and dx = W^T y + state injection (k_inject)   (msckf.h:1373-1418).
+//     W = L^-1 [T''P | r'']   fused into the factorisation: every worker CTA keeps its share of the right-hand-side columns
+//                             as rows in shared memory and treats them as extra panel rows
+// followed by  P <- P - W^T W, dx = W^T y and the state injection (k_syrk, all SMs)   (msckf.h:1373-1418).
+// Two forms: k_tail_fused<S, 2> -- a cluster of 9 CTAs (non-portable size, used where the device accepts it): CTA 0 runs S''s
+// chain of diagonal blocks, CTA 1 Gamma's, CTAs 2..8 are the workers; k_tail_fused<S, 1> -- a cluster of 8: CTA 0 runs both
+// chains (tf_factor_block), CTAs 1..7 are the workers.
 //
 // What bounds this kernel is latency, not the FP64 pipe (64 lane-FMA/clk/SM measured, scripts/fp64_rate.cu): a chain of
-// ~n dependent pivots at ~8 cycles per dependent instruction, plus instruction fetch -- the kernel is ~100 KB of SASS, the
-// L1.5 instruction cache holds 32 KB, so every phase of every block iteration starts cold (5-7 cycles per instruction).
-// Measured (ncu source view, %globaltimer stamps, profiles/) and acted upon:
-//   * the diagonal block (tail_diag.cuh): blocked by panels of 4 columns over the whole CTA, the 4 x 4 micro-blocks of both
-//     matrices factorised redundantly in registers by the threads that solve the panel rows, keep / drop decisions evaluated
-//     by all of them from the same numbers -- no per-pivot shuffle, flag or poll; inverses built block row by block row;
-//     every loop rolled except the micro-block (a fully unrolled 8 x 8 / 32-step-inverse version was fetch-bound: 21 us);
-//   * work on the critical path: the panel below a diagonal block is X = A_panel L_kk^-T.  With L_kk^-1 at hand the
-//     panel is a small GEMM shared by all 8 warps instead of a 32-step substitution per row; panel rows are dealt to
-//     the 8 CTAs (no redundant solves) and exchanged through L2 (a scratch panel every CTA reads back after the cluster
-//     barrier: ~64 B/clk per SM, against ~20 B/clk for pushing it into 8 shared memories through DSMEM);
+// n dependent pivots at 80 cycles each (scripts/fp64_latency.cu) plus what surrounds them, and instruction fetch -- the kernel
+// is ~100 KB of SASS, the L1.5 instruction cache holds 32 KB, so every phase of every block iteration starts cold.
+// Measured (ncu source view, %globaltimer stamps, profiles/r02_tail_stamps.md) and acted upon:
+//   * the diagonal block (tail_diag.cuh): blocked by panels (8 columns in the two-chain form, 4 in the one-chain form), the
+//     diagonal micro-block factorised redundantly in registers by the threads that solve the panel rows, keep / drop decisions
+//     evaluated by all of them from the same numbers; the inverses ride along as 32 extra rows; loops rolled except the
+//     micro-block (a fully unrolled 32-step-inverse version was fetch-bound: 21 us per block against 8 now);
+//   * the two chains only meet in the keep / drop flags: one 32-bit word per panel through DSMEM, S'' speculates "nothing
+//     dropped" and repeats a micro-block only when Gamma did drop (tf_factor_one);
+//   * the chain CTAs run ONE BLOCK AHEAD of the workers: they solve the 32 panel rows of the next diagonal block themselves
+//     with the inverses they still hold, form that block and factorise it while the workers solve the panel, exchange it and
+//     run the trailing update (split cluster barrier: arrive early, wait late; published inverses double-buffered);
+//   * the panel below a diagonal block is X = A_panel L_kk^-T: with L_kk^-1 at hand a small GEMM shared by all 8 warps
+//     instead of a 32-step substitution per row; panel rows are dealt to the workers (no redundant solves) and exchanged
+//     through L2 (a scratch panel every worker reads back after the cluster barrier: ~64 B/clk per SM, against ~20 B/clk
+//     for pushing it into 8 shared memories through DSMEM);
 //   * shared-memory bank conflicts: tiles are dealt so that the lanes of a warp read neighbouring columns.
-//   * overlap: CTA 0 forms the leading 32 x 32 tile of the trailing update itself and factorises the NEXT diagonal block
-//     while CTAs 1..7 run the rest of the trailing update and their share of the substitution.
 // Two cluster barriers (release/acquire at cluster scope) per block order the phases.
 #pragma once
 #include <cooperative_groups.h>
